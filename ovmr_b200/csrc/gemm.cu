@@ -1,0 +1,340 @@
+// ovmr_b200 — persistent, warp-specialised tcgen05/TMEM GEMM for sm_100a.
+//
+// Serves every dense contraction on the OVMR hot path: QKV / out-proj / MLP of the
+// CLIP towers and the visual-token generator (reference: nn.MultiheadAttention +
+// nn.Linear inside clip/model.py:167-194, 219-252), the patch-embed conv as a GEMM
+// over patchified pixels (clip/model.py:366, 412-414), the CLS / EOT projections
+// (clip/model.py:423-426, 827-831) and the cosine-logit head
+// (trainers/mm_classifier_one_prompt.py:263-265, 358-360).
+//
+// Structure (one CTA per SM, 256 threads):
+//   warp 0 / lane 0 : TMA producer   — A[128x64] + B[BLOCK_N x 64] bf16 tiles, 128B swizzle
+//   warp 1 / lane 0 : UMMA issuer    — tcgen05.mma 128 x BLOCK_N x 16, fp32 accum in TMEM
+//   warp 2          : TMEM allocator
+//   warps 4..7      : epilogue       — tcgen05.ld -> bias/QuickGELU/residual -> global
+// Pipelines: smem ring (full/empty mbarriers, TMA <-> UMMA) and a 2-deep TMEM
+// accumulator ring (tmem_full/tmem_empty, UMMA <-> epilogue) so the epilogue of
+// tile i overlaps the main loop of tile i+1.
+#include "gemm.cuh"
+
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ovmr {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (256 or 512)
+  static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + align slack
+};
+
+__device__ __forceinline__ float quick_gelu(float x) {
+  // x * sigmoid(1.702 x)
+  return x / (1.0f + __expf(-1.702f * x));
+}
+
+template <int BLOCK_N, int OUT_BF16>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    int M, int N, int K, GemmEpilogue ep) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-B alignment
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8u * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int total_tiles = m_tiles * n_tiles;
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== UMMA issuer =====================
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M, BLOCK_N);
+      uint32_t stage = 0, phase = 0, iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t a_desc = umma_desc_k_sw128(sa);
+          const uint64_t b_desc = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-B units
+            umma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(tfull_bar(as));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter this warp may read
+    uint32_t iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int m = m_blk * BLOCK_M + ew * 32 + lane;
+      const bool row_ok = m < M;
+      long long orow = m, rrow = m;
+      if (ep.row_grp > 0) {
+        const int img = m / ep.row_grp, t = m % ep.row_grp;
+        orow = static_cast<long long>(img) * (ep.row_grp + 1) + 1 + t;
+        rrow = 1 + t;
+      }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+        if (c0 == BLOCK_N - 32) {
+          // accumulator fully in registers: hand the TMEM stage back to the issuer
+          tc_fence_before();
+          mbar_arrive(tempty_bar(as));
+        }
+        const int n0 = n_blk * BLOCK_N + c0;
+        if (!row_ok || n0 >= N) continue;
+        if (OUT_BF16) {
+          __nv_bfloat16* orow_ptr = reinterpret_cast<__nv_bfloat16*>(ep.out) + orow * ep.ldo;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const int n = n0 + j;
+            if (n + 8 > N) break;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = ep.alpha * __uint_as_float(v[j + e]);
+            if (ep.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
+              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            }
+            if (ep.act == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = quick_gelu(x[e]);
+            }
+            if (ep.resid) {
+              const float* r = ep.resid + rrow * ep.ldr + n;
+              const float4 r0 = *reinterpret_cast<const float4*>(r);
+              const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
+              x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+              x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+            }
+            uint4 o;
+            o.x = pack_bf16x2(x[0], x[1]);
+            o.y = pack_bf16x2(x[2], x[3]);
+            o.z = pack_bf16x2(x[4], x[5]);
+            o.w = pack_bf16x2(x[6], x[7]);
+            *reinterpret_cast<uint4*>(orow_ptr + n) = o;
+          }
+        } else {
+          float* orow_ptr = reinterpret_cast<float*>(ep.out) + orow * ep.ldo;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + j;
+            if (n + 4 > N) break;
+            float4 x;
+            x.x = ep.alpha * __uint_as_float(v[j + 0]);
+            x.y = ep.alpha * __uint_as_float(v[j + 1]);
+            x.z = ep.alpha * __uint_as_float(v[j + 2]);
+            x.w = ep.alpha * __uint_as_float(v[j + 3]);
+            if (ep.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+              x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+            }
+            if (ep.act == 1) {
+              x.x = quick_gelu(x.x); x.y = quick_gelu(x.y);
+              x.z = quick_gelu(x.z); x.w = quick_gelu(x.w);
+            }
+            if (ep.resid) {
+              const float4 r = *reinterpret_cast<const float4*>(ep.resid + rrow * ep.ldr + n);
+              x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+            }
+            *reinterpret_cast<float4*>(orow_ptr + n) = x;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+  });
+  return fn;
+}
+
+// bf16 row-major [rows, cols] (cols contiguous, leading dim ld) -> tiles of box_rows x 64, 128B swizzle
+int make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
+                   int box_rows) {
+  auto enc = tensor_map_encoder();
+  if (!enc) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    return OVMR_ERR_INVALID;
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d) base=%p rows=%lld cols=%lld ld=%lld box_rows=%d",
+                   (int)r, base, rows, cols, ld, box_rows);
+    return OVMR_ERR_INVALID;
+  }
+  return 0;
+}
+
+template <int BLOCK_N, int OUT_BF16>
+int launch(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+           const GemmEpilogue& ep, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, A, M, K, lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, B, N, K, ldb, BLOCK_N);
+  if (rc) return rc;
+  auto kern = gemm_bf16_tn_kernel<BLOCK_N, OUT_BF16>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    OVMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int total = m_tiles * n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+  OVMR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                 const GemmEpilogue& ep, cudaStream_t stream, int force_block_n) {
+  OVMR_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  OVMR_REQUIRE(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0,
+               "gemm: K, N, lda, ldb must be multiples of 8 (K=%d N=%d lda=%lld ldb=%lld)", K, N, lda, ldb);
+  OVMR_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0,
+               "gemm: operands must be 16-byte aligned");
+  OVMR_REQUIRE(ep.out != nullptr && ep.ldo >= N, "gemm: bad output (ldo=%lld, N=%d)", ep.ldo, N);
+  int bn = force_block_n;
+  if (bn == 0) {
+    // wave-quantisation heuristic: cost ~ waves x tile width
+    const int sms = num_sms();
+    const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    const long long w256 = (m_tiles * ((N + 255) / 256) + sms - 1) / sms * 256;
+    const long long w128 = (m_tiles * ((N + 127) / 128) + sms - 1) / sms * 128;
+    bn = (w256 <= w128 + w128 / 16) ? 256 : 128;
+  }
+  OVMR_REQUIRE(bn == 128 || bn == 256, "gemm: block_n must be 128 or 256 (got %d)", bn);
+  if (bn == 256) {
+    return ep.out_bf16 ? launch<256, 1>(A, lda, B, ldb, M, N, K, ep, stream)
+                       : launch<256, 0>(A, lda, B, ldb, M, N, K, ep, stream);
+  }
+  return ep.out_bf16 ? launch<128, 1>(A, lda, B, ldb, M, N, K, ep, stream)
+                     : launch<128, 0>(A, lda, B, ldb, M, N, K, ep, stream);
+}
+
+}  // namespace ovmr

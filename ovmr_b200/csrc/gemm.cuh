@@ -1,0 +1,36 @@
+// ovmr_b200 — host-side declaration of the tcgen05 GEMM launcher.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ovmr {
+
+// C[M,N] = epilogue(alpha * A[M,K] . B[N,K]^T)  — "TN" GEMM, both operands K-major
+// (A = activations, row-major; B = nn.Linear weight [out,in], row-major).
+//
+// epilogue:  v = alpha*acc + bias[n];  v = act(v);  v += resid[rrow, n];  out[orow, n] = v
+//   * out is bf16 (out_bf16=1) or fp32 (out_bf16=0)
+//   * act: 0 none, 1 QuickGELU  x*sigmoid(1.702x)      (clip/model.py:162-164)
+//   * row_grp = 0: orow = rrow = m.
+//     row_grp = G>0 (patch-embed scatter): orow = (m/G)*(G+1) + 1 + m%G, rrow = 1 + m%G,
+//     i.e. patch token m of image m/G lands behind that image's CLS row and `resid`
+//     is the positional-embedding table (clip/model.py:412-416).
+struct GemmEpilogue {
+  const float* bias = nullptr;   // [N] fp32
+  const float* resid = nullptr;  // fp32, leading dim ldr (may alias out)
+  long long ldr = 0;
+  void* out = nullptr;
+  long long ldo = 0;
+  int out_bf16 = 1;
+  int act = 0;
+  float alpha = 1.0f;
+  int row_grp = 0;
+};
+
+// A: bf16 [M,K] leading dim lda (elements); B: bf16 [N,K] leading dim ldb.
+// Requirements: K % 8 == 0, N % 8 == 0, lda/ldb % 8 == 0, 16-byte aligned bases.
+// force_block_n: 0 = heuristic, else 128 or 256.
+int gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                 const GemmEpilogue& ep, cudaStream_t stream, int force_block_n = 0);
+
+}  // namespace ovmr

@@ -1,0 +1,32 @@
+// ovmr_b200 — tiny host runtime shared by all kernels: last-error string, device props.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace ovmr {
+
+static thread_local char g_last_error[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+const char* last_error() { return g_last_error; }
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace ovmr
