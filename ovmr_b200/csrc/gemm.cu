@@ -7,11 +7,12 @@
 // (clip/model.py:423-426, 827-831) and the cosine-logit head
 // (trainers/mm_classifier_one_prompt.py:263-265, 358-360).
 //
-// Structure (one CTA per SM, 256 threads):
+// Structure (one CTA per SM, 384 threads):
 //   warp 0 / lane 0 : TMA producer   — A[128x64] + B[BLOCK_N x 64] bf16 tiles, 128B swizzle
 //   warp 1 / lane 0 : UMMA issuer    — tcgen05.mma 128 x BLOCK_N x 16, fp32 accum in TMEM
 //   warp 2          : TMEM allocator
-//   warps 4..7      : epilogue       — tcgen05.ld -> bias/QuickGELU/residual -> global
+//   warps 4..11     : epilogue       — tcgen05.ld -> smem transpose -> bias/QuickGELU/residual
+//                                       -> coalesced global stores
 // Pipelines: smem ring (full/empty mbarriers, TMA <-> UMMA) and a 2-deep TMEM
 // accumulator ring (tmem_full/tmem_empty, UMMA <-> epilogue) so the epilogue of
 // tile i overlaps the main loop of tile i+1.
@@ -30,7 +31,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -40,12 +41,16 @@ struct GemmCfg {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (256 or 512)
   static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + align slack
+  static constexpr uint32_t STG_BYTES = 8 * 32 * 128;  // per-epilogue-warp 32 x 128 B transpose buffers
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;  // + align slack
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
-  // x * sigmoid(1.702 x)
-  return x / (1.0f + __expf(-1.702f * x));
+  // x * sigmoid(1.702 x) with sigmoid(y) = 0.5 + 0.5 tanh(y/2): one MUFU op per element
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 template <int BLOCK_N, int OUT_BF16>
@@ -59,14 +64,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t stg_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = stg_base + Cfg::STG_BYTES;
   auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
   auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8u * (2 * STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES + 8u * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,7 +93,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), 256);
     }
     mbar_fence_init();
   }
@@ -144,92 +150,99 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter this warp may read
+    // ===================== epilogue (8 warps) =====================
+    // A warp may only read the TMEM lane quarter (warp % 4); warps w and w+4 share a quarter
+    // and split the tile's columns in halves.
+    const int ew = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int HALF_N = BLOCK_N / 2;
+    constexpr int CHUNKS = HALF_N / 32;
+    const uint32_t stg = stg_base + (warp - 4) * 4096;
+    // Coalesced mapping used for all global traffic: lane -> (sub-row lane/8, 16-B column
+    // chunk lane%8); one warp instruction then touches 4 rows x 128 contiguous bytes.
+    const int sub = lane >> 3, cj = lane & 7;
     uint32_t iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
+      const int row0 = m_blk * BLOCK_M + ew * 32;
+      const int ncol0 = n_blk * BLOCK_N + half * HALF_N + 4 * cj;  // + 32*c per chunk
+      // bias for all of this lane's columns, fetched while the main loop is still running
+      float4 bv[CHUNKS];
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int n = ncol0 + 32 * c;
+        bv[c] = (ep.bias && n + 4 <= N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int m = m_blk * BLOCK_M + ew * 32 + lane;
-      const bool row_ok = m < M;
-      long long orow = m, rrow = m;
-      if (ep.row_grp > 0) {
-        const int img = m / ep.row_grp, t = m % ep.row_grp;
-        orow = static_cast<long long>(img) * (ep.row_grp + 1) + 1 + t;
-        rrow = 1 + t;
-      }
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c0, v);
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N + half * HALF_N;
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr, v);
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int n = ncol0 + 32 * c;  // this lane's 4 output columns
+        const bool col_ok = n + 4 <= N;
+        // residual prefetch (overlaps the TMEM load + staging)
+        float4 rv[8];
+        if (ep.resid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = row0 + 4 * i + sub;
+            rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && col_ok) {
+              const long long rrow = ep.row_grp > 0 ? 1 + m % ep.row_grp : m;
+              rv[i] = *reinterpret_cast<const float4*>(ep.resid + rrow * ep.ldr + n);
+            }
+          }
+        }
         tmem_ld_wait();
-        if (c0 == BLOCK_N - 32) {
-          // accumulator fully in registers: hand the TMEM stage back to the issuer
+        __syncwarp();  // previous chunk's read-back finished
+        // stage: TMEM lane (= tile row) `lane` -> 128-B smem row, 16-B chunks XOR-swizzled by row
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[4 * j]),
+                       "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                       : "memory");
+        }
+        if (c + 1 < CHUNKS) {
+          tmem_ld_32x32b_x32(taddr + 32 * (c + 1), v);  // in flight during the emit phase
+        } else {
+          // accumulator fully drained: hand the TMEM stage back to the issuer
           tc_fence_before();
           mbar_arrive(tempty_bar(as));
         }
-        const int n0 = n_blk * BLOCK_N + c0;
-        if (!row_ok || n0 >= N) continue;
-        if (OUT_BF16) {
-          __nv_bfloat16* orow_ptr = reinterpret_cast<__nv_bfloat16*>(ep.out) + orow * ep.ldo;
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const int n = n0 + j;
-            if (n + 8 > N) break;
-            float x[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = ep.alpha * __uint_as_float(v[j + e]);
-            if (ep.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
-              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-            }
-            if (ep.act == 1) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = quick_gelu(x[e]);
-            }
-            if (ep.resid) {
-              const float* r = ep.resid + rrow * ep.ldr + n;
-              const float4 r0 = *reinterpret_cast<const float4*>(r);
-              const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
-              x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
-              x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
-            }
-            uint4 o;
-            o.x = pack_bf16x2(x[0], x[1]);
-            o.y = pack_bf16x2(x[2], x[3]);
-            o.z = pack_bf16x2(x[4], x[5]);
-            o.w = pack_bf16x2(x[6], x[7]);
-            *reinterpret_cast<uint4*>(orow_ptr + n) = o;
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + sub;
+          const int m = row0 + r;
+          float4 x;
+          const uint32_t src = stg + r * 128 + ((cj ^ (r & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                       : "r"(src)
+                       : "memory");
+          if (m >= M || !col_ok) continue;
+          x.x = fmaf(ep.alpha, x.x, bv[c].x); x.y = fmaf(ep.alpha, x.y, bv[c].y);
+          x.z = fmaf(ep.alpha, x.z, bv[c].z); x.w = fmaf(ep.alpha, x.w, bv[c].w);
+          if (ep.act == 1) {
+            x.x = quick_gelu(x.x); x.y = quick_gelu(x.y);
+            x.z = quick_gelu(x.z); x.w = quick_gelu(x.w);
           }
-        } else {
-          float* orow_ptr = reinterpret_cast<float*>(ep.out) + orow * ep.ldo;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = n0 + j;
-            if (n + 4 > N) break;
-            float4 x;
-            x.x = ep.alpha * __uint_as_float(v[j + 0]);
-            x.y = ep.alpha * __uint_as_float(v[j + 1]);
-            x.z = ep.alpha * __uint_as_float(v[j + 2]);
-            x.w = ep.alpha * __uint_as_float(v[j + 3]);
-            if (ep.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-              x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
-            }
-            if (ep.act == 1) {
-              x.x = quick_gelu(x.x); x.y = quick_gelu(x.y);
-              x.z = quick_gelu(x.z); x.w = quick_gelu(x.w);
-            }
-            if (ep.resid) {
-              const float4 r = *reinterpret_cast<const float4*>(ep.resid + rrow * ep.ldr + n);
-              x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
-            }
-            *reinterpret_cast<float4*>(orow_ptr + n) = x;
+          if (ep.resid) { x.x += rv[i].x; x.y += rv[i].y; x.z += rv[i].z; x.w += rv[i].w; }
+          long long orow = m;
+          if (ep.row_grp > 0) orow = static_cast<long long>(m / ep.row_grp) * (ep.row_grp + 1) + 1 + m % ep.row_grp;
+          if (OUT_BF16) {
+            uint2 o;
+            o.x = pack_bf16x2(x.x, x.y);
+            o.y = pack_bf16x2(x.z, x.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + orow * ep.ldo + n) = o;
+          } else {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow * ep.ldo + n) = x;
           }
         }
       }
