@@ -1,0 +1,176 @@
+/* ovmr_b200 — C-ABI of the B200-native OVMR hot path (libovmr_b200.so).
+ *
+ * The reference (Zehong-Ma/OVMR) is pure Python/PyTorch and has no FFI of its own; its boundary for
+ * this path is the Python API of `clip/` and `trainers/mm_classifier_one_prompt.py`.  This header is
+ * the layer directly UNDER that API: every entry point replaces the arithmetic of one reference
+ * function and is what `ovmr_b200/clip/model.py` and `ovmr_b200/trainers/mm_classifier_one_prompt.py`
+ * bind through ctypes (see INTEGRATION.md for the reference-side binding).
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, sizes, a cudaStream_t passed as void*; no torch types.
+ *   - every function returns 0 on success, otherwise a non-zero status (a cudaError_t value, or
+ *     OVMR_ERR_INVALID for argument errors); ovmr_last_error() gives the message (thread-local).
+ *   - stream-explicit and re-entrant per stream; no global mutable state besides per-process
+ *     kernel-attribute caches.  Nothing here allocates device memory: callers pass workspaces.
+ *   - activations are token-major: a tower input of n_seq sequences x seq_len tokens is the fp32
+ *     matrix [n_seq*seq_len, width] (the reference's [L, N, D] permuted; same arithmetic).
+ *   - GEMM operands (weights, row-major [out, in] exactly as nn.Linear stores them, and the activations
+ *     the kernels produce) are 16-bit: bf16 or IEEE fp16, chosen per tower (`ovmr_transformer.fp16`) or
+ *     per call (`fp16` argument).  The ".._w bf16" comments below mean "16-bit in that format".
+ *     Accumulation, the residual stream, LayerNorm / softmax statistics, biases and embeddings are fp32.
+ */
+#ifndef OVMR_B200_H_
+#define OVMR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define OVMR_OK 0
+#define OVMR_ERR_INVALID 10001
+#define OVMR_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- introspection */
+int ovmr_abi_version(void);
+const char* ovmr_last_error(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+long long ovmr_launch_count(void);
+
+/* ---------------------------------------------------------------- weight descriptors */
+/* One pre-LN residual block: ResidualAttentionBlock / ResidualAttentionBlockWithDropout
+ * (clip/model.py:167-194, 219-252).  State-dict names in comments. */
+typedef struct ovmr_block_weights {
+  const float* ln1_w;  const float* ln1_b;      /* ln_1.weight / ln_1.bias            [D]      */
+  const void*  qkv_w;  const float* qkv_b;      /* attn.in_proj_weight bf16 [3D,D] / in_proj_bias [3D] */
+  const void*  out_w;  const float* out_b;      /* attn.out_proj.weight bf16 [D,D] / bias [D]  */
+  const float* ln2_w;  const float* ln2_b;      /* ln_2.*                              [D]      */
+  const void*  fc_w;   const float* fc_b;       /* mlp.c_fc.weight bf16 [4D,D] / bias [4D]     */
+  const void*  proj_w; const float* proj_b;     /* mlp.c_proj.weight bf16 [D,4D] / bias [D]    */
+} ovmr_block_weights;
+
+/* Transformer / TransformerDropout (clip/model.py:261-269, 341-350). `blocks` is a HOST array. */
+typedef struct ovmr_transformer {
+  int width, heads, layers;
+  int fp16;                        /* 16-bit operand format of this tower's GEMM weights and activations:
+                                      0 = bf16, 1 = IEEE fp16 (the reference's shipped precision) */
+  const ovmr_block_weights* blocks;
+} ovmr_transformer;
+
+/* VisionTransformer (clip/model.py:360-380). */
+typedef struct ovmr_vit {
+  int resolution, patch, width, embed_dim;
+  int k_pad;                       /* 3*patch*patch rounded up to a multiple of 8 (row pitch of conv_w) */
+  const void*  conv_w;             /* conv1.weight.reshape(D,-1) bf16 [D, k_pad], zero padded            */
+  const float* class_embedding;    /* [D]                                                                */
+  const float* positional_embedding; /* [1+G*G, D]                                                       */
+  const float* ln_pre_w;  const float* ln_pre_b;
+  const float* ln_post_w; const float* ln_post_b;
+  const void*  proj_t;             /* visual.proj^T bf16 [E, D]                                           */
+  ovmr_transformer transformer;
+} ovmr_vit;
+
+/* Text tower tail (clip/model.py:755-771). */
+typedef struct ovmr_text {
+  int width, embed_dim, context_length;
+  const float* positional_embedding; /* [context_length, W] */
+  const float* ln_final_w; const float* ln_final_b;
+  const void*  text_projection_t;  /* text_projection^T bf16 [E, W] */
+  ovmr_transformer transformer;
+} ovmr_text;
+
+/* ---------------------------------------------------------------- towers */
+/* Workspace (bytes) the tower calls below need for `rows` tokens of width `width`. */
+size_t ovmr_transformer_workspace_bytes(long long rows, int width);
+size_t ovmr_vit_workspace_bytes(const ovmr_vit* v, int batch);
+size_t ovmr_text_workspace_bytes(const ovmr_text* t, int n_seq, int seq_len);
+
+/* Transformer.forward / TransformerDropout.forward in eval mode (clip/model.py:268-269, 349-350):
+ * x fp32 [n_seq*seq_len, width], updated in place.  causal!=0 = build_attention_mask (:802-808). */
+int ovmr_transformer_forward(const ovmr_transformer* t, float* x, int n_seq, int seq_len, int causal,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* CLIP.encode_image = VisionTransformer.forward (clip/model.py:411-428, 814-815):
+ * images fp32 NCHW [batch,3,R,R] -> features fp32 [batch, E]; normalize!=0 additionally applies
+ * x / x.norm(dim=-1) (trainers/mm_classifier_one_prompt.py:244, 307). */
+int ovmr_vit_forward(const ovmr_vit* v, const float* images, int batch, float* features, int normalize,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Tail shared by CLIP.encode_text (clip/model.py:824-831) and TextEncoder.forward
+ * (trainers/mm_classifier_one_prompt.py:82-89): x fp32 [n_seq*seq_len, W] already holds
+ * embeddings + positional_embedding (see ovmr_build_text_rows); causal transformer, ln_final,
+ * gather token eos_index[n] of sequence n, @ text_projection -> features fp32 [n_seq, E].
+ * seq_len may be shorter than context_length as long as it exceeds max(eos_index): under the
+ * causal mask the read-out token cannot see later positions. */
+int ovmr_text_forward(const ovmr_text* t, float* x, const int* eos_index, int n_seq, int seq_len,
+                      float* features, int normalize, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- kernels (also used directly by tests) */
+/* out = epilogue(alpha * A[M,K] . B[N,K]^T): bias[n] add, act (0 none / 1 QuickGELU clip/model.py:162-164),
+ * fp32 residual add, bf16 or fp32 store.  row_grp>0 = patch-embed scatter (see csrc/gemm.cuh). */
+int ovmr_gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                 const float* bias, const float* resid, long long ldr, void* out, long long ldo,
+                 int out_16bit, int act, float alpha, int row_grp, int force_block_n, int fp16, void* stream);
+
+/* LayerNorm (clip/model.py:153-159), eps 1e-5, fp32 statistics. Source row of output row r is
+ * r*gather_mul + (gather ? gather[r] : 0).  Outputs fp32 and/or bf16; optional chained second LN. */
+int ovmr_layernorm(const float* x, long long ldx, int rows, int width, const int* gather, long long gather_mul,
+                   const float* w, const float* b, float* out_f32, long long ld_f32, void* out_bf16,
+                   long long ld_bf16, const float* w2, const float* b2, int fp16, void* stream);
+
+/* nn.MultiheadAttention core (clip/model.py:184-189): qkv bf16 [n_seq*L, 3D] -> out bf16 [n_seq*L, D]. */
+int ovmr_attention(const void* qkv, void* out, int n_seq, int seq_len, int width, int heads, int causal,
+                   int fp16, void* stream);
+
+/* conv1 input as GEMM operand (clip/model.py:412-414): fp32 NCHW -> bf16 [batch*G*G, ldo]. */
+int ovmr_patchify(const float* images, void* out_16bit, int batch, int resolution, int patch, int ldo, int fp16,
+                  void* stream);
+
+/* Text-tower input rows: out[(n*L+t),:] = src(n,t) + positional_embedding[t].
+ *   mode 0: token_embedding[ids[n*ids_ld+t]]                       (clip/model.py:821-823)
+ *   mode 1: prompts[n, t, :] of a [N, src_L, W] tensor              (trainers/...:81)
+ *   mode 2: update_prompts splice (trainers/...:156-157) of table[label[n]] (or row block 0 if
+ *           label==NULL / label[n]<0, the "a ." template) with vtok[n, 0..n_ctx)                 */
+int ovmr_build_text_rows(float* out, const float* table, const float* pos, const int* ids, int ids_ld,
+                         const int* label, const float* vtok, int n_ctx, int n_seq, int seq_len, int src_len,
+                         int width, int mode, void* stream);
+
+/* PromptLearner.forward aggregator input (trainers/...:167-168): [C, n_ctx+S, E] = [cls_token ; feats[c]]. */
+int ovmr_agg_build(float* out, const float* cls_token, const float* feats, int n_cls, int shots, int n_ctx,
+                   int embed_dim, void* stream);
+/* out[g, j, :] = in[g*T + j, :], j < take  (first n_ctx aggregator outputs, trainers/...:169). */
+int ovmr_take_rows(float* out, const float* in, long long groups, int T, int take, int width, void* stream);
+
+/* x / x.norm(dim=-1, keepdim=True) (trainers/...:204, 208, 244, 307); out_f32 may alias x. */
+int ovmr_l2norm(const float* x, long long rows, int width, float* out_f32, void* out_bf16, void* stream);
+/* F.normalize(x.mean(dim=1)) over [G, T, E] (trainers/...:124, 210-211; T templates/prompts per class). */
+int ovmr_segmented_mean(const float* in, long long groups, int T, int width, float* out, int normalize, void* stream);
+/* fp32 [rows,E] -> bf16 [out_rows,3E] hi/lo split (order 0: hi|hi|lo, order 1: hi|lo|hi; extra rows zero). */
+int ovmr_split_bf16(const float* x, long long rows, int width, void* out, int order, long long out_rows, void* stream);
+
+/* Eval branch of CustomCLIP.forward (trainers/...:348-363) + evaluator top-k (dassl/evaluation/evaluator.py:54-58).
+ * logits fp32 [rows, ld]; classifier s at columns [s*seg_stride, s*seg_stride+C); nseg 3 = fusion with
+ * fusion_w [C,3] (mm, v, t), nseg 1 = single softmax.  probs [rows, ldp] may be NULL (top-k only). */
+int ovmr_fusion_softmax_topk(const float* logits, long long rows, long long ld, int seg_stride, int nseg, int n_cls,
+                             const float* fusion_w, float* probs, long long ldp, int k, int* top_idx,
+                             float* top_val, void* stream);
+/* argmax per (row, classifier segment), ties -> lowest index (trainers/...:268-270 via torcheval). */
+int ovmr_argmax_segments(const float* logits, long long rows, long long ld, int seg_stride, int nseg, int n_cls,
+                         int* pred, void* stream);
+/* counts int32 [n_cls*nseg (tp) | n_cls*nseg (num_pred) | n_cls (num_label)], caller-zeroed; accumulates. */
+int ovmr_f1_counts(const int* pred, const int* labels, long long rows, int nseg, int n_cls, int* counts, void* stream);
+/* F1 per class and classifier + softmax(tau*F1) (trainers/...:268-274). f1_out may be NULL. */
+int ovmr_fusion_weights(const int* counts, int nseg, int n_cls, float tau, float* f1_out, float* w_out, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVMR_B200_H_ */

@@ -1,0 +1,276 @@
+// ovmr_b200 — C-ABI entry points (include/ovmr_b200.h) and the tower drivers that string the
+// sm_100a kernels together: Transformer.forward, VisionTransformer.forward, the text read-out.
+#include "../../include/ovmr_b200.h"
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "head.cuh"
+#include "rowops.cuh"
+
+namespace ovmr {
+const char* last_error();
+long long launch_count();
+}  // namespace ovmr
+
+using ovmr::GemmEpilogue;
+
+namespace {
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
+
+struct TransformerWs {
+  void* a_bf16;    // [rows, D]   LayerNorm output / attention output (GEMM A operands)
+  void* big_bf16;  // [rows, 4D]  QKV (3D) and MLP hidden (4D), never live together
+  size_t bytes;
+};
+
+TransformerWs carve_transformer_ws(void* base, long long rows, int width) {
+  TransformerWs w;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  const size_t a = align256(static_cast<size_t>(rows) * width * 2);
+  const size_t b = align256(static_cast<size_t>(rows) * width * 4 * 2);
+  w.a_bf16 = p;
+  w.big_bf16 = p + a;
+  w.bytes = a + b;
+  return w;
+}
+
+#define RET_IF(expr)        \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc) return _rc;    \
+  } while (0)
+
+int check_transformer(const ovmr_transformer* t) {
+  OVMR_REQUIRE(t != nullptr && t->blocks != nullptr, "transformer: null descriptor");
+  OVMR_REQUIRE(t->layers > 0 && t->heads > 0 && t->width == t->heads * 64,
+               "transformer: width must equal heads*64 (width=%d heads=%d)", t->width, t->heads);
+  OVMR_REQUIRE(t->width % 128 == 0 && t->width <= 1024, "transformer: width=%d must be a multiple of 128, <= 1024",
+               t->width);
+  return 0;
+}
+
+// One pre-LN residual block on the fp32 residual stream x [rows, D] (clip/model.py:191-194).
+int run_block(const ovmr_block_weights& bw, float* x, int n_seq, int seq_len, int D, int heads, int causal,
+              int fp16, const TransformerWs& ws, bool ln1_done, cudaStream_t st) {
+  const int rows = n_seq * seq_len;
+  // x + attn(ln_1(x))
+  if (!ln1_done)
+    RET_IF(ovmr::layernorm(x, D, rows, D, nullptr, 0, bw.ln1_w, bw.ln1_b, nullptr, 0, ws.a_bf16, D, nullptr, nullptr, fp16, st));
+  GemmEpilogue qkv;
+  qkv.bias = bw.qkv_b; qkv.out = ws.big_bf16; qkv.ldo = 3LL * D; qkv.out_bf16 = 1; qkv.fp16 = fp16;
+  RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.qkv_w, D, rows, 3 * D, D, qkv, st));
+  RET_IF(ovmr::attention(ws.big_bf16, ws.a_bf16, n_seq, seq_len, D, heads, causal, fp16, st));
+  GemmEpilogue op;
+  op.bias = bw.out_b; op.resid = x; op.ldr = D; op.out = x; op.ldo = D; op.out_bf16 = 0; op.fp16 = fp16;
+  RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.out_w, D, rows, D, D, op, st));
+  // x + c_proj(QuickGELU(c_fc(ln_2(x))))
+  RET_IF(ovmr::layernorm(x, D, rows, D, nullptr, 0, bw.ln2_w, bw.ln2_b, nullptr, 0, ws.a_bf16, D, nullptr, nullptr, fp16, st));
+  GemmEpilogue fc;
+  fc.bias = bw.fc_b; fc.out = ws.big_bf16; fc.ldo = 4LL * D; fc.out_bf16 = 1; fc.act = 1; fc.fp16 = fp16;
+  RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.fc_w, D, rows, 4 * D, D, fc, st));
+  GemmEpilogue pj;
+  pj.bias = bw.proj_b; pj.resid = x; pj.ldr = D; pj.out = x; pj.ldo = D; pj.out_bf16 = 0; pj.fp16 = fp16;
+  RET_IF(ovmr::gemm_tn(ws.big_bf16, 4LL * D, bw.proj_w, 4LL * D, rows, D, 4 * D, pj, st));
+  return 0;
+}
+
+int run_transformer(const ovmr_transformer* t, float* x, int n_seq, int seq_len, int causal, void* wsp,
+                    size_t ws_bytes, bool first_ln1_done, cudaStream_t st) {
+  RET_IF(check_transformer(t));
+  OVMR_REQUIRE(n_seq > 0 && seq_len > 0, "transformer: empty input (n_seq=%d seq_len=%d)", n_seq, seq_len);
+  const long long rows = static_cast<long long>(n_seq) * seq_len;
+  OVMR_REQUIRE(rows < (1LL << 31), "transformer: too many tokens");
+  OVMR_REQUIRE(wsp != nullptr && ws_bytes >= ovmr_transformer_workspace_bytes(rows, t->width),
+               "transformer: workspace too small (%zu < %zu)", ws_bytes, ovmr_transformer_workspace_bytes(rows, t->width));
+  const TransformerWs ws = carve_transformer_ws(wsp, rows, t->width);
+  for (int l = 0; l < t->layers; ++l) {
+    RET_IF(run_block(t->blocks[l], x, n_seq, seq_len, t->width, t->heads, causal, t->fp16 != 0, ws,
+                     l == 0 && first_ln1_done, st));
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ovmr_abi_version(void) { return OVMR_ABI_VERSION; }
+const char* ovmr_last_error(void) { return ovmr::last_error(); }
+long long ovmr_launch_count(void) { return ovmr::launch_count(); }
+
+size_t ovmr_transformer_workspace_bytes(long long rows, int width) {
+  return align256(static_cast<size_t>(rows) * width * 2) + align256(static_cast<size_t>(rows) * width * 8);
+}
+
+size_t ovmr_vit_workspace_bytes(const ovmr_vit* v, int batch) {
+  if (!v || batch <= 0) return 0;
+  const int G = v->resolution / v->patch, L = G * G + 1;
+  const long long rows = static_cast<long long>(batch) * L;
+  return align256(static_cast<size_t>(rows) * v->width * 4)        // x fp32
+         + ovmr_transformer_workspace_bytes(rows, v->width)        // a / big
+         + align256(static_cast<size_t>(batch) * v->width * 2)     // ln_post(CLS) bf16
+         + align256(static_cast<size_t>(batch) * G * G * v->k_pad * 2);  // patchified pixels bf16
+}
+
+size_t ovmr_text_workspace_bytes(const ovmr_text* t, int n_seq, int seq_len) {
+  if (!t || n_seq <= 0 || seq_len <= 0) return 0;
+  return ovmr_transformer_workspace_bytes(static_cast<long long>(n_seq) * seq_len, t->width) +
+         align256(static_cast<size_t>(n_seq) * t->width * 2);
+}
+
+int ovmr_transformer_forward(const ovmr_transformer* t, float* x, int n_seq, int seq_len, int causal, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  OVMR_REQUIRE(x != nullptr, "transformer_forward: null x");
+  return run_transformer(t, x, n_seq, seq_len, causal, workspace, workspace_bytes, false, S(stream));
+}
+
+int ovmr_vit_forward(const ovmr_vit* v, const float* images, int batch, float* features, int normalize,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  OVMR_REQUIRE(v && images && features && workspace, "vit_forward: null argument");
+  OVMR_REQUIRE(batch > 0, "vit_forward: batch=%d", batch);
+  OVMR_REQUIRE(v->patch > 0 && v->resolution >= v->patch, "vit_forward: bad geometry");
+  RET_IF(check_transformer(&v->transformer));
+  const int D = v->width, E = v->embed_dim;
+  OVMR_REQUIRE(D == v->transformer.width && E % 8 == 0, "vit_forward: width mismatch / embed_dim %% 8");
+  const int G = v->resolution / v->patch, L = G * G + 1;
+  const long long rows = static_cast<long long>(batch) * L;
+  OVMR_REQUIRE(v->k_pad >= 3 * v->patch * v->patch && v->k_pad % 8 == 0, "vit_forward: k_pad=%d invalid", v->k_pad);
+  OVMR_REQUIRE(workspace_bytes >= ovmr_vit_workspace_bytes(v, batch), "vit_forward: workspace too small (%zu < %zu)",
+               workspace_bytes, ovmr_vit_workspace_bytes(v, batch));
+  cudaStream_t st = S(stream);
+  uint8_t* p = reinterpret_cast<uint8_t*>(workspace);
+  float* x = reinterpret_cast<float*>(p);
+  p += align256(static_cast<size_t>(rows) * D * 4);
+  void* tws = p;
+  const size_t tws_bytes = ovmr_transformer_workspace_bytes(rows, D);
+  const TransformerWs ws = carve_transformer_ws(tws, rows, D);
+  p += tws_bytes;
+  void* cls_bf16 = p;
+  p += align256(static_cast<size_t>(batch) * D * 2);
+  void* patches = p;
+
+  // conv1 as a GEMM over patchified pixels; epilogue adds positional_embedding[1+t] and scatters
+  // patch t of image b to row b*L + 1 + t; CLS rows = class_embedding + positional_embedding[0].
+  const int fp16 = v->transformer.fp16 != 0;
+  RET_IF(ovmr::patchify(images, patches, batch, v->resolution, v->patch, v->k_pad, fp16, st));
+  RET_IF(ovmr::cls_rows(x, v->class_embedding, v->positional_embedding, batch, L, D, st));
+  GemmEpilogue pe;
+  pe.resid = v->positional_embedding; pe.ldr = D; pe.out = x; pe.ldo = D; pe.out_bf16 = 0; pe.row_grp = G * G; pe.fp16 = fp16;
+  RET_IF(ovmr::gemm_tn(patches, v->k_pad, v->conv_w, v->k_pad, batch * G * G, D, v->k_pad, pe, st));
+  // ln_pre (fp32, in place) chained with layer 0's ln_1 (bf16 operand of the first QKV GEMM)
+  const ovmr_block_weights& b0 = v->transformer.blocks[0];
+  RET_IF(ovmr::layernorm(x, D, static_cast<int>(rows), D, nullptr, 0, v->ln_pre_w, v->ln_pre_b, x, D, ws.a_bf16, D,
+                         b0.ln1_w, b0.ln1_b, fp16, st));
+  RET_IF(run_transformer(&v->transformer, x, batch, L, 0, tws, tws_bytes, true, st));
+  // ln_post on the CLS rows, projection, optional L2 normalisation
+  RET_IF(ovmr::layernorm(x, D, batch, D, nullptr, L, v->ln_post_w, v->ln_post_b, nullptr, 0, cls_bf16, D, nullptr,
+                         nullptr, fp16, st));
+  GemmEpilogue pr;
+  pr.out = features; pr.ldo = E; pr.out_bf16 = 0; pr.fp16 = fp16;
+  RET_IF(ovmr::gemm_tn(cls_bf16, D, v->proj_t, D, batch, E, D, pr, st));
+  if (normalize) RET_IF(ovmr::l2norm(features, batch, E, features, nullptr, st));
+  return 0;
+}
+
+int ovmr_text_forward(const ovmr_text* t, float* x, const int* eos_index, int n_seq, int seq_len, float* features,
+                      int normalize, void* workspace, size_t workspace_bytes, void* stream) {
+  OVMR_REQUIRE(t && x && eos_index && features && workspace, "text_forward: null argument");
+  OVMR_REQUIRE(n_seq > 0 && seq_len > 0 && seq_len <= t->context_length, "text_forward: n_seq=%d seq_len=%d", n_seq,
+               seq_len);
+  RET_IF(check_transformer(&t->transformer));
+  const int W = t->width, E = t->embed_dim;
+  OVMR_REQUIRE(W == t->transformer.width && E % 8 == 0, "text_forward: width mismatch");
+  OVMR_REQUIRE(workspace_bytes >= ovmr_text_workspace_bytes(t, n_seq, seq_len), "text_forward: workspace too small");
+  cudaStream_t st = S(stream);
+  const long long rows = static_cast<long long>(n_seq) * seq_len;
+  const size_t tws_bytes = ovmr_transformer_workspace_bytes(rows, W);
+  void* eot_bf16 = reinterpret_cast<uint8_t*>(workspace) + tws_bytes;
+  RET_IF(run_transformer(&t->transformer, x, n_seq, seq_len, 1, workspace, tws_bytes, false, st));
+  const int fp16 = t->transformer.fp16 != 0;
+  RET_IF(ovmr::layernorm(x, W, n_seq, W, eos_index, seq_len, t->ln_final_w, t->ln_final_b, nullptr, 0, eot_bf16, W,
+                         nullptr, nullptr, fp16, st));
+  GemmEpilogue pr;
+  pr.out = features; pr.ldo = E; pr.out_bf16 = 0; pr.fp16 = fp16;
+  RET_IF(ovmr::gemm_tn(eot_bf16, W, t->text_projection_t, W, n_seq, E, W, pr, st));
+  if (normalize) RET_IF(ovmr::l2norm(features, n_seq, E, features, nullptr, st));
+  return 0;
+}
+
+int ovmr_gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const float* bias,
+                 const float* resid, long long ldr, void* out, long long ldo, int out_16bit, int act, float alpha,
+                 int row_grp, int force_block_n, int fp16, void* stream) {
+  GemmEpilogue ep;
+  ep.bias = bias; ep.resid = resid; ep.ldr = ldr; ep.out = out; ep.ldo = ldo; ep.out_bf16 = out_16bit;
+  ep.act = act; ep.alpha = alpha; ep.row_grp = row_grp; ep.fp16 = fp16 != 0;
+  return ovmr::gemm_tn(A, lda, B, ldb, M, N, K, ep, S(stream), force_block_n);
+}
+
+int ovmr_layernorm(const float* x, long long ldx, int rows, int width, const int* gather, long long gather_mul,
+                   const float* w, const float* b, float* out_f32, long long ld_f32, void* out_bf16, long long ld_bf16,
+                   const float* w2, const float* b2, int fp16, void* stream) {
+  return ovmr::layernorm(x, ldx, rows, width, gather, gather_mul, w, b, out_f32, ld_f32, out_bf16, ld_bf16, w2, b2,
+                         fp16 != 0, S(stream));
+}
+
+int ovmr_attention(const void* qkv, void* out, int n_seq, int seq_len, int width, int heads, int causal, int fp16,
+                   void* stream) {
+  return ovmr::attention(qkv, out, n_seq, seq_len, width, heads, causal, fp16 != 0, S(stream));
+}
+
+int ovmr_patchify(const float* images, void* out_16bit, int batch, int resolution, int patch, int ldo, int fp16,
+                  void* stream) {
+  return ovmr::patchify(images, out_16bit, batch, resolution, patch, ldo, fp16 != 0, S(stream));
+}
+
+int ovmr_build_text_rows(float* out, const float* table, const float* pos, const int* ids, int ids_ld, const int* label,
+                         const float* vtok, int n_ctx, int n_seq, int seq_len, int src_len, int width, int mode,
+                         void* stream) {
+  return ovmr::build_text_rows(out, table, pos, ids, ids_ld, label, vtok, n_ctx, n_seq, seq_len, src_len, width, mode,
+                               S(stream));
+}
+
+int ovmr_agg_build(float* out, const float* cls_token, const float* feats, int n_cls, int shots, int n_ctx, int embed_dim,
+                   void* stream) {
+  return ovmr::agg_build(out, cls_token, feats, n_cls, shots, n_ctx, embed_dim, S(stream));
+}
+
+int ovmr_take_rows(float* out, const float* in, long long groups, int T, int take, int width, void* stream) {
+  return ovmr::take_rows(out, in, groups, T, take, width, S(stream));
+}
+
+int ovmr_l2norm(const float* x, long long rows, int width, float* out_f32, void* out_bf16, void* stream) {
+  return ovmr::l2norm(x, rows, width, out_f32, out_bf16, S(stream));
+}
+
+int ovmr_segmented_mean(const float* in, long long groups, int T, int width, float* out, int normalize, void* stream) {
+  return ovmr::segmented_mean(in, groups, T, width, out, normalize, S(stream));
+}
+
+int ovmr_split_bf16(const float* x, long long rows, int width, void* out, int order, long long out_rows, void* stream) {
+  return ovmr::split_bf16(x, rows, width, out, order, out_rows, S(stream));
+}
+
+int ovmr_fusion_softmax_topk(const float* logits, long long rows, long long ld, int seg_stride, int nseg, int n_cls,
+                             const float* fusion_w, float* probs, long long ldp, int k, int* top_idx, float* top_val,
+                             void* stream) {
+  return ovmr::fusion_softmax_topk(logits, rows, ld, seg_stride, nseg, n_cls, fusion_w, probs, ldp, k, top_idx, top_val,
+                                   S(stream));
+}
+
+int ovmr_argmax_segments(const float* logits, long long rows, long long ld, int seg_stride, int nseg, int n_cls, int* pred,
+                         void* stream) {
+  return ovmr::argmax_segments(logits, rows, ld, seg_stride, nseg, n_cls, pred, S(stream));
+}
+
+int ovmr_f1_counts(const int* pred, const int* labels, long long rows, int nseg, int n_cls, int* counts, void* stream) {
+  return ovmr::f1_counts(pred, labels, rows, nseg, n_cls, counts, S(stream));
+}
+
+int ovmr_fusion_weights(const int* counts, int nseg, int n_cls, float tau, float* f1_out, float* w_out, void* stream) {
+  return ovmr::fusion_weights(counts, nseg, n_cls, tau, f1_out, w_out, S(stream));
+}
+
+}  // extern "C"

@@ -8,6 +8,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -19,6 +20,7 @@ namespace ovmr {
 // ----------------------------------------------------------------------------
 void set_last_error(const char* fmt, ...);
 int num_sms();
+void count_launches(int n);  // bookkeeping for ovmr_launch_count()
 
 #define OVMR_CHECK_CUDA(expr)                                                     \
   do {                                                                            \
@@ -66,6 +68,15 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// 16-bit operand format of a pipeline: bf16 (fp16 == 0) or IEEE fp16 (fp16 != 0)
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int fp16) {
+  return fp16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
 }
 
 // ----------------------------------------------------------------------------
@@ -220,11 +231,11 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;           // SWIZZLE_128B
   return d;
 }
-// UMMA instruction descriptor, kind::f16: bf16 A/B (both K-major), fp32 accumulate.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
+// UMMA instruction descriptor, kind::f16: A/B both bf16 (fp16 == 0) or both fp16, K-major, fp32 accumulate.
+__host__ __device__ constexpr uint32_t umma_idesc_16b_f32(int M, int N, int fp16) {
   return (1u << 4)                               // D format  = f32
-         | (1u << 7)                             // A format  = bf16
-         | (1u << 10)                            // B format  = bf16
+         | ((fp16 ? 0u : 1u) << 7)               // A format  : 0 = f16, 1 = bf16
+         | ((fp16 ? 0u : 1u) << 10)              // B format
          | (static_cast<uint32_t>(N >> 3) << 17) // N / 8
          | (static_cast<uint32_t>(M >> 4) << 24);// M / 16
 }

@@ -55,7 +55,7 @@ __device__ __forceinline__ float quick_gelu(float x) {
 
 template <int BLOCK_N, int OUT_BF16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     int M, int N, int K, GemmEpilogue ep) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
@@ -125,7 +125,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== UMMA issuer =====================
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M, BLOCK_N);
+      const uint32_t idesc = umma_idesc_16b_f32(BLOCK_M, BLOCK_N, ep.fp16);
       uint32_t stage = 0, phase = 0, iter = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
         const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
@@ -238,8 +238,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (ep.row_grp > 0) orow = static_cast<long long>(m / ep.row_grp) * (ep.row_grp + 1) + 1 + m % ep.row_grp;
           if (OUT_BF16) {
             uint2 o;
-            o.x = pack_bf16x2(x.x, x.y);
-            o.y = pack_bf16x2(x.z, x.w);
+            o.x = pack16x2(x.x, x.y, ep.fp16);
+            o.y = pack16x2(x.z, x.w, ep.fp16);
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + orow * ep.ldo + n) = o;
           } else {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow * ep.ldo + n) = x;
@@ -306,7 +306,7 @@ int launch(const void* A, long long lda, const void* B, long long ldb, int M, in
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, B, N, K, ldb, BLOCK_N);
   if (rc) return rc;
-  auto kern = gemm_bf16_tn_kernel<BLOCK_N, OUT_BF16>;
+  auto kern = gemm_tn_kernel<BLOCK_N, OUT_BF16>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -318,12 +318,13 @@ int launch(const void* A, long long lda, const void* B, long long ldb, int M, in
   const int grid = total < num_sms() ? total : num_sms();
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
   OVMR_CHECK_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
 }  // namespace
 
-int gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                  const GemmEpilogue& ep, cudaStream_t stream, int force_block_n) {
   OVMR_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   OVMR_REQUIRE(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0,

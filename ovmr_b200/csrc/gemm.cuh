@@ -25,12 +25,13 @@ struct GemmEpilogue {
   int act = 0;
   float alpha = 1.0f;
   int row_grp = 0;
+  int fp16 = 0;  // 16-bit format of A, B and of a 16-bit output: 0 = bf16, 1 = IEEE fp16
 };
 
-// A: bf16 [M,K] leading dim lda (elements); B: bf16 [N,K] leading dim ldb.
+// A: 16-bit [M,K] leading dim lda (elements); B: 16-bit [N,K] leading dim ldb (format: ep.fp16).
 // Requirements: K % 8 == 0, N % 8 == 0, lda/ldb % 8 == 0, 16-byte aligned bases.
 // force_block_n: 0 = heuristic, else 128 or 256.
-int gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                  const GemmEpilogue& ep, cudaStream_t stream, int force_block_n = 0);
 
 }  // namespace ovmr

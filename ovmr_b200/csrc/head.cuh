@@ -1,0 +1,15 @@
+// ovmr_b200 — classification-head launchers (see head.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ovmr {
+
+int fusion_softmax_topk(const float* logits, long long rows, long long ld, int seg_stride, int nseg, int C,
+                        const float* fusion_w, float* probs, long long ldp, int k, int* top_idx, float* top_val,
+                        cudaStream_t stream);
+int argmax_segments(const float* logits, long long rows, long long ld, int seg_stride, int nseg, int C, int* pred,
+                    cudaStream_t stream);
+int f1_counts(const int* pred, const int* labels, long long rows, int nseg, int C, int* counts, cudaStream_t stream);
+int fusion_weights(const int* counts, int nseg, int C, float tau, float* f1_out, float* w_out, cudaStream_t stream);
+
+}  // namespace ovmr

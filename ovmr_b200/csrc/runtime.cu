@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace ovmr {
@@ -16,6 +18,10 @@ void set_last_error(const char* fmt, ...) {
 }
 
 const char* last_error() { return g_last_error; }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
   static int cached[64] = {0};

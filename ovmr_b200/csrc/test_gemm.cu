@@ -87,7 +87,7 @@ static int run_case(const Case& c) {
   ep.act = c.act;
   ep.alpha = c.alpha;
   ep.row_grp = c.row_grp;
-  int rc = ovmr::gemm_bf16_tn(dA, K, dB, K, M, N, K, ep, 0, c.block_n);
+  int rc = ovmr::gemm_tn(dA, K, dB, K, M, N, K, ep, 0, c.block_n);
   if (rc) {
     printf("[%s] launch failed rc=%d: %s\n", c.name, rc, ovmr::last_error());
     return 1;
@@ -143,9 +143,9 @@ static int run_case(const Case& c) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) ovmr::gemm_bf16_tn(dA, K, dB, K, M, N, K, ep, 0, c.block_n);
+    for (int i = 0; i < 3; ++i) ovmr::gemm_tn(dA, K, dB, K, M, N, K, ep, 0, c.block_n);
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < c.time_iters; ++i) ovmr::gemm_bf16_tn(dA, K, dB, K, M, N, K, ep, 0, c.block_n);
+    for (int i = 0; i < c.time_iters; ++i) ovmr::gemm_tn(dA, K, dB, K, M, N, K, ep, 0, c.block_n);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms;

@@ -1,0 +1,249 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C-ABI (ctypes) and
+compared with plain fp32 torch / the oracle on the same seeded inputs.
+
+Tolerances: bf16-operand GEMMs and attention are checked relatively (bf16 has 8 mantissa bits:
+|err| <= 2^-7 |ref| + small abs); fp32 row kernels to 1e-5; integer outputs bit-exact."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+from tests.helpers import O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _lib():
+    from ovmr_b200 import _lib as L
+    return L, L.lib()
+
+
+def _bf16r(x):
+    return x.bfloat16().float()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (200, 384, 768, 0), (1000, 768, 3072, 256),
+                                      (333, 3000, 1536, 0), (50, 512, 512, 128), (4097, 2304, 768, 256)])
+@pytest.mark.parametrize("mode", ["bf16_bias", "bf16_gelu", "f32_resid", "fp16_gelu", "fp16_f32_resid"])
+def test_gemm(M, N, K, bn, mode):
+    L, lib = _lib()
+    fp16 = int(mode.startswith("fp16"))
+    t16 = torch.float16 if fp16 else torch.bfloat16
+    mode = {"fp16_gelu": "bf16_gelu", "fp16_f32_resid": "f32_resid"}.get(mode, mode)
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    a = _bf16r(torch.randn(M, K, generator=g))
+    w = _bf16r(torch.randn(N, K, generator=g) * 0.05)
+    bias = torch.randn(N, generator=g)
+    resid = torch.randn(M, N, generator=g)
+    ref = a.double() @ w.double().t() + bias.double()
+    if mode == "bf16_gelu":
+        ref = ref * torch.sigmoid(1.702 * ref)
+    if mode == "f32_resid":
+        ref = ref + resid.double()
+    A, W, Bi = a.to(DEV).to(t16), w.to(DEV).to(t16), bias.to(DEV)
+    if mode == "f32_resid":
+        out = resid.to(DEV).clone()  # in place, like the residual stream
+        L.check(lib.ovmr_gemm_tn(A.data_ptr(), K, W.data_ptr(), K, M, N, K, Bi.data_ptr(), out.data_ptr(), N,
+                                 out.data_ptr(), N, 0, 0, 1.0, 0, bn, fp16, L.stream()))
+        torch.cuda.synchronize()
+        assert (out.cpu().double() - ref).abs().max() < 2e-3
+    else:
+        out = torch.zeros(M, N, dtype=t16, device=DEV)
+        L.check(lib.ovmr_gemm_tn(A.data_ptr(), K, W.data_ptr(), K, M, N, K, Bi.data_ptr(), None, 0,
+                                 out.data_ptr(), N, 1, int(mode == "bf16_gelu"), 1.0, 0, bn, fp16, L.stream()))
+        torch.cuda.synchronize()
+        err = (out.cpu().double() - ref).abs()
+        assert (err <= ref.abs() * 2 ** -7 + 4e-3).all(), float(err.max())
+
+
+def test_gemm_rejects_bad_arguments():
+    L, lib = _lib()
+    a = torch.zeros(8, 12, dtype=torch.bfloat16, device=DEV)
+    rc = lib.ovmr_gemm_tn(a.data_ptr(), 12, a.data_ptr(), 12, 8, 8, 12, None, None, 0, a.data_ptr(), 8, 1, 0, 1.0,
+                          0, 0, 0, L.stream())
+    assert rc != 0 and b"multiples of 8" in lib.ovmr_last_error()
+    rc = lib.ovmr_gemm_tn(a.data_ptr(), 16, a.data_ptr(), 16, 0, 8, 16, None, None, 0, a.data_ptr(), 8, 1, 0, 1.0,
+                          0, 0, 0, L.stream())
+    assert rc != 0
+
+
+@pytest.mark.parametrize("rows,D", [(1, 128), (197 * 3, 768), (77 * 5, 512), (1000, 1024)])
+def test_layernorm(rows, D):
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(rows + D)
+    x = torch.randn(rows, D, generator=g) * 3 + 0.5
+    w, b = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    ref = O.layer_norm(x, w, b)
+    X, W, B = x.to(DEV), w.to(DEV), b.to(DEV)
+    o32 = torch.empty_like(X)
+    o16 = torch.empty(rows, D, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.ovmr_layernorm(X.data_ptr(), D, rows, D, None, 0, W.data_ptr(), B.data_ptr(), o32.data_ptr(), D,
+                               o16.data_ptr(), D, None, None, 0, L.stream()))
+    torch.cuda.synchronize()
+    assert (o32.cpu() - ref).abs().max() < 2e-5
+    assert torch.equal(o16.cpu(), o32.cpu().bfloat16())
+
+
+def test_layernorm_gather_and_chain():
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(5)
+    n, Lq, D = 7, 9, 256
+    x = torch.randn(n * Lq, D, generator=g)
+    w, b, w2, b2 = (torch.randn(D, generator=g) for _ in range(4))
+    idx = torch.tensor([0, 8, 3, 5, 1, 7, 2], dtype=torch.int32)
+    ref = O.layer_norm(x.view(n, Lq, D)[torch.arange(n), idx.long()], w, b)
+    X = x.to(DEV)
+    I, W, B, W2, B2 = idx.to(DEV), w.to(DEV), b.to(DEV), w2.to(DEV), b2.to(DEV)  # keep the device copies alive
+    o16 = torch.empty(n, D, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.ovmr_layernorm(X.data_ptr(), D, n, D, I.data_ptr(), Lq, W.data_ptr(), B.data_ptr(), None, 0,
+                               o16.data_ptr(), D, None, None, 0, L.stream()))
+    torch.cuda.synchronize()
+    assert (o16.cpu().float() - ref).abs().max() < 3e-2
+    # chained: out32 = LN1(x) in place, out16 = LN2(LN1(x))
+    ref1 = O.layer_norm(x, w, b)
+    ref2 = O.layer_norm(ref1, w2, b2)
+    X2 = x.to(DEV)
+    o16 = torch.empty(n * Lq, D, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.ovmr_layernorm(X2.data_ptr(), D, n * Lq, D, None, 0, W.data_ptr(), B.data_ptr(), X2.data_ptr(), D,
+                               o16.data_ptr(), D, W2.data_ptr(), B2.data_ptr(), 0, L.stream()))
+    torch.cuda.synchronize()
+    assert (X2.cpu() - ref1).abs().max() < 2e-5
+    assert (o16.cpu().float() - ref2).abs().max() < 4e-2
+
+
+@pytest.mark.parametrize("n_seq,Lq,heads,causal", [(3, 197, 12, 0), (5, 77, 8, 1), (4, 6, 2, 0), (2, 18, 8, 0),
+                                                   (2, 8, 8, 1), (1, 577, 16, 0), (2, 64, 2, 1), (2, 65, 2, 1)])
+@pytest.mark.parametrize("fp16", [0, 1])
+def test_attention(n_seq, Lq, heads, causal, fp16):
+    L, lib = _lib()
+    t16 = torch.float16 if fp16 else torch.bfloat16
+    D = heads * 64
+    g = torch.Generator().manual_seed(n_seq * 1000 + Lq)
+    qkv = _bf16r(torch.randn(n_seq * Lq, 3 * D, generator=g))
+    q, k, v = (t.view(n_seq, Lq, heads, 64).transpose(1, 2) for t in qkv.split(D, dim=-1))
+    s = (q @ k.transpose(-1, -2)) / 8.0
+    if causal:
+        s = s + torch.full((Lq, Lq), float("-inf")).triu_(1)
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(n_seq * Lq, D)
+    QKV = qkv.to(DEV).to(t16)
+    out = torch.zeros(n_seq * Lq, D, dtype=t16, device=DEV)
+    L.check(lib.ovmr_attention(QKV.data_ptr(), out.data_ptr(), n_seq, Lq, D, heads, causal, fp16, L.stream()))
+    torch.cuda.synchronize()
+    err = (out.cpu().float() - ref).abs().max().item()
+    assert err < (4e-3 if fp16 else 2e-2), err
+
+
+@pytest.mark.parametrize("B,R,P", [(3, 64, 16), (2, 224, 16), (2, 224, 14), (1, 224, 32)])
+def test_patchify(B, R, P):
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(B + R + P)
+    img = torch.randn(B, 3, R, R, generator=g)
+    G = R // P
+    k = 3 * P * P
+    kpad = (k + 7) // 8 * 8
+    ref = img.reshape(B, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(B * G * G, k).bfloat16()
+    out = torch.full((B * G * G, kpad), 7.0, dtype=torch.bfloat16, device=DEV)
+    IMG = img.to(DEV)
+    L.check(lib.ovmr_patchify(IMG.data_ptr(), out.data_ptr(), B, R, P, kpad, 0, L.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu()[:, :k], ref)
+    assert (out.cpu()[:, k:] == 0).all()
+
+
+def test_l2norm_split_mean():
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 512, generator=g)
+    X = x.to(DEV)
+    o32 = torch.empty_like(X)
+    o16 = torch.empty(37, 512, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.ovmr_l2norm(X.data_ptr(), 37, 512, o32.data_ptr(), o16.data_ptr(), L.stream()))
+    torch.cuda.synchronize()
+    assert (o32.cpu() - O.l2n(x)).abs().max() < 1e-6
+    # hi/lo split reconstructs fp32 to ~2^-16 relative
+    sp = torch.empty(40, 3 * 512, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.ovmr_split_bf16(X.data_ptr(), 37, 512, sp.data_ptr(), 1, 40, L.stream()))
+    torch.cuda.synchronize()
+    s = sp.cpu().float()
+    assert (s[37:] == 0).all()
+    assert torch.equal(s[:37, :512], s[:37, 1024:])
+    assert ((s[:37, :512] + s[:37, 512:1024]) - x).abs().max() < 2 ** -15 * x.abs().max()
+    # segmented mean + normalise
+    y = torch.randn(11, 5, 128, generator=g)
+    out = torch.empty(11, 128, device=DEV)
+    Y = y.to(DEV)
+    L.check(lib.ovmr_segmented_mean(Y.data_ptr(), 11, 5, 128, out.data_ptr(), 1, L.stream()))
+    torch.cuda.synchronize()
+    assert (out.cpu() - torch.nn.functional.normalize(y.mean(1), dim=-1)).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("R,Cn,k", [(64, 10, 1), (33, 1000, 5), (5, 21841, 3)])
+def test_fusion_softmax_topk(R, Cn, k):
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(R + Cn)
+    Cpad = (Cn + 7) // 8 * 8
+    logits = torch.randn(R, 3 * Cpad, generator=g) * 3
+    fw = torch.softmax(torch.randn(Cn, 3, generator=g), -1)
+    segs = [logits[:, s * Cpad:s * Cpad + Cn] for s in range(3)]
+    ref = sum(torch.softmax(segs[s], -1) * fw[:, s] for s in range(3))
+    probs = torch.empty(R, Cn, device=DEV)
+    idx = torch.empty(R, k, dtype=torch.int32, device=DEV)
+    val = torch.empty(R, k, device=DEV)
+    LG, FW = logits.to(DEV), fw.to(DEV)
+    L.check(lib.ovmr_fusion_softmax_topk(LG.data_ptr(), R, 3 * Cpad, Cpad, 3, Cn, FW.data_ptr(),
+                                         probs.data_ptr(), Cn, k, idx.data_ptr(), val.data_ptr(), L.stream()))
+    torch.cuda.synchronize()
+    assert (probs.cpu() - ref).abs().max() < 2e-6
+    # top-k must be exactly the top-k of the probabilities the kernel itself emitted (ties -> lowest index)
+    oi, ov = O.topk(probs.cpu(), k)
+    assert torch.equal(idx.cpu().long(), oi)
+    assert torch.equal(val.cpu(), ov)
+    # single-softmax mode (text / vision / multimodal)
+    p1 = torch.empty(R, Cn, device=DEV)
+    L.check(lib.ovmr_fusion_softmax_topk(LG.data_ptr(), R, 3 * Cpad, Cpad, 1, Cn, None, p1.data_ptr(), Cn,
+                                         k, idx.data_ptr(), val.data_ptr(), L.stream()))
+    torch.cuda.synchronize()
+    assert (p1.cpu() - torch.softmax(segs[0], -1)).abs().max() < 2e-6
+
+
+def test_topk_ties_lowest_index():
+    L, lib = _lib()
+    logits = torch.zeros(4, 24)
+    logits[1, 5] = logits[1, 3] = 2.0
+    idx = torch.empty(4, 2, dtype=torch.int32, device=DEV)
+    val = torch.empty(4, 2, device=DEV)
+    LG = logits.to(DEV)
+    L.check(lib.ovmr_fusion_softmax_topk(LG.data_ptr(), 4, 24, 24, 1, 20, None, None, 20, 2,
+                                         idx.data_ptr(), val.data_ptr(), L.stream()))
+    torch.cuda.synchronize()
+    assert idx.cpu().tolist() == [[0, 1], [3, 5], [0, 1], [0, 1]]
+
+
+def test_f1_fusion_weights_match_oracle():
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(11)
+    Cn, S = 37, 5
+    R = Cn * S
+    Cpad = 40
+    labels = torch.arange(Cn).repeat_interleave(S)
+    logits = torch.randn(R, 3 * Cpad, generator=g)
+    logits[torch.arange(R), labels] += 2.0           # classifier 0 is good
+    logits[torch.arange(R), Cpad + labels] += 0.7    # classifier 1 is mediocre
+    preds = torch.empty(R, 3, dtype=torch.int32, device=DEV)
+    LG, LAB = logits.to(DEV), labels.int().to(DEV)
+    L.check(lib.ovmr_argmax_segments(LG.data_ptr(), R, 3 * Cpad, Cpad, 3, Cn, preds.data_ptr(), L.stream()))
+    ref_pred = torch.stack([logits[:, s * Cpad:s * Cpad + Cn].argmax(1) for s in range(3)], -1)
+    torch.cuda.synchronize()
+    assert torch.equal(preds.cpu().long(), ref_pred)
+    counts = torch.zeros(2 * Cn * 3 + Cn, dtype=torch.int32, device=DEV)
+    L.check(lib.ovmr_f1_counts(preds.data_ptr(), LAB.data_ptr(), R, 3, Cn, counts.data_ptr(), L.stream()))
+    f1 = torch.empty(Cn, 3, device=DEV)
+    w = torch.empty(Cn, 3, device=DEV)
+    L.check(lib.ovmr_fusion_weights(counts.data_ptr(), 3, Cn, 10.0, f1.data_ptr(), w.data_ptr(), L.stream()))
+    torch.cuda.synchronize()
+    ref_f1 = torch.stack([O.multiclass_f1(ref_pred[:, s], labels, Cn) for s in range(3)], -1)
+    assert torch.equal(f1.cpu(), ref_f1)  # integer counts + IEEE divisions: bit exact
+    assert (w.cpu() - (10.0 * ref_f1).softmax(-1)).abs().max() < 1e-6
