@@ -41,6 +41,13 @@ int ovmr_abi_version(void);
 const char* ovmr_last_error(void);
 /* number of kernels launched by this library in this process (bench.py's gpu_launches) */
 long long ovmr_launch_count(void);
+/* Optional device-side timing per kernel class (bench.py's roofline leg). While enabled every launch is
+ * bracketed by two CUDA events on its stream.  Classes: 0 GEMM (work = algorithmic FLOPs 2MNK),
+ * 1 attention (FLOPs), 2 LayerNorm (bytes), 3 patchify (bytes), 4 fusion-softmax/top-k (bytes).
+ * ovmr_profile_enable(1) resets and starts, (0) stops; ovmr_profile_summary synchronises the recorded
+ * events and fills elapsed milliseconds, summed work and launch counts for classes [0, ncat). */
+int ovmr_profile_enable(int on);
+int ovmr_profile_summary(double* ms, double* work, long long* launches, int ncat);
 
 /* ---------------------------------------------------------------- weight descriptors */
 /* One pre-LN residual block: ResidualAttentionBlock / ResidualAttentionBlockWithDropout

@@ -42,6 +42,8 @@ SIGNATURES = {
     "ovmr_abi_version": (c_int, []),
     "ovmr_last_error": (C.c_char_p, []),
     "ovmr_launch_count": (c_ll, []),
+    "ovmr_profile_enable": (c_int, [c_int]),
+    "ovmr_profile_summary": (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll), c_int]),
     "ovmr_transformer_workspace_bytes": (c_size_t, [c_ll, c_int]),
     "ovmr_vit_workspace_bytes": (c_size_t, [C.POINTER(Vit), c_int]),
     "ovmr_text_workspace_bytes": (c_size_t, [C.POINTER(Text), c_int, c_int]),
@@ -121,3 +123,19 @@ def stream():
 
 def launch_count() -> int:
     return int(load().ovmr_launch_count())
+
+
+PROFILE_CLASSES = ("gemm", "attention", "layernorm", "patchify", "head")
+
+
+def profile_enable(on: bool):
+    check(load().ovmr_profile_enable(int(on)), "ovmr_profile_enable")
+
+
+def profile_summary() -> dict:
+    """{class: {"ms": elapsed, "work": FLOPs or bytes, "launches": n}} for the launches recorded since
+    profile_enable(True).  Synchronises."""
+    n = len(PROFILE_CLASSES)
+    ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (c_ll * n)()
+    check(load().ovmr_profile_summary(ms, work, cnt, n), "ovmr_profile_summary")
+    return {name: {"ms": ms[i], "work": work[i], "launches": int(cnt[i])} for i, name in enumerate(PROFILE_CLASSES)}

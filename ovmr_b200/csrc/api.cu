@@ -11,6 +11,8 @@
 namespace ovmr {
 const char* last_error();
 long long launch_count();
+void prof_enable(bool on);
+int prof_summary(double* ms, double* work, long long* launches, int ncat);
 }  // namespace ovmr
 
 using ovmr::GemmEpilogue;
@@ -100,6 +102,14 @@ extern "C" {
 int ovmr_abi_version(void) { return OVMR_ABI_VERSION; }
 const char* ovmr_last_error(void) { return ovmr::last_error(); }
 long long ovmr_launch_count(void) { return ovmr::launch_count(); }
+int ovmr_profile_enable(int on) {
+  ovmr::prof_enable(on != 0);
+  return 0;
+}
+int ovmr_profile_summary(double* ms, double* work, long long* launches, int ncat) {
+  OVMR_REQUIRE(ms && work && launches && ncat > 0, "profile_summary: null argument");
+  return ovmr::prof_summary(ms, work, launches, ncat);
+}
 
 size_t ovmr_transformer_workspace_bytes(long long rows, int width) {
   return align256(static_cast<size_t>(rows) * width * 2) + align256(static_cast<size_t>(rows) * width * 8);

@@ -227,6 +227,7 @@ int attention(const void* qkv, void* out, int n_seq, int L, int D, int heads, in
   }
   const dim3 grid((L + QT - 1) / QT, heads, n_seq);
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+  ProfScope prof(PROF_ATTENTION, 4.0 * n_seq * heads * static_cast<double>(L) * L * HD * (causal ? 0.5 : 1.0), stream);
   if (fp16)
     attention_kernel<true><<<grid, 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                          reinterpret_cast<__nv_bfloat16*>(out), L, D, causal, scale_log2e);

@@ -22,6 +22,18 @@ void set_last_error(const char* fmt, ...);
 int num_sms();
 void count_launches(int n);  // bookkeeping for ovmr_launch_count()
 
+// kernel classes for the optional device-side timing (see runtime.cu)
+enum ProfCat { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_ROWOPS = 3, PROF_HEAD = 4, PROF_NCAT = 5 };
+bool profiling();
+void prof_begin(int cat, double work, cudaStream_t s);
+void prof_end(cudaStream_t s);
+struct ProfScope {
+  cudaStream_t s;
+  bool on;
+  ProfScope(int cat, double work, cudaStream_t st) : s(st), on(profiling()) { if (on) prof_begin(cat, work, s); }
+  ~ProfScope() { if (on) prof_end(s); }
+};
+
 #define OVMR_CHECK_CUDA(expr)                                                     \
   do {                                                                            \
     cudaError_t _e = (expr);                                                      \

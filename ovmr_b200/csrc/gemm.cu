@@ -316,6 +316,7 @@ int launch(const void* A, long long lda, const void* B, long long ldb, int M, in
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
+  ProfScope prof(PROF_GEMM, 2.0 * M * N * K, stream);  // work = algorithmic FLOPs
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
   OVMR_CHECK_CUDA(cudaGetLastError());
   count_launches(1);

@@ -177,6 +177,7 @@ int fusion_softmax_topk(const float* logits, long long rows, long long ld, int s
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(fusion_softmax_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  ProfScope prof(PROF_HEAD, static_cast<double>(rows) * (4.0 * nseg * C + (probs ? 4.0 * C : 0.0) + 8.0 * k), stream);
   fusion_softmax_topk_kernel<<<static_cast<int>(rows), HEAD_THREADS, smem, stream>>>(
       logits, ld, seg_stride, nseg, C, fusion_w, probs, ldp, k, top_idx, top_val);
   OVMR_CHECK_CUDA(cudaGetLastError());

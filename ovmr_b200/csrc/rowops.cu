@@ -297,6 +297,8 @@ int layernorm(const float* x, long long ldx, int rows, int D, const int* gather,
   const int warps = 8;
   const int grid = (rows + warps - 1) / warps;
   auto* o16 = reinterpret_cast<__nv_bfloat16*>(out16);
+  // work = algorithmic bytes: fp32 row read + whichever outputs are written
+  ProfScope prof(PROF_LAYERNORM, static_cast<double>(rows) * D * (4.0 + (out32 ? 4.0 : 0.0) + (out16 ? 2.0 : 0.0)), stream);
 #define LN_CASE(NV)                                                                                     \
   case NV:                                                                                              \
     layernorm_kernel<NV><<<grid, warps * 32, 0, stream>>>(x, ldx, rows, gather, gather_mul, w, b, out32, \
@@ -317,6 +319,7 @@ int patchify(const float* images, void* out, int B, int R, int P, int ldo, int f
   OVMR_REQUIRE(ldo >= K && ldo % 8 == 0, "patchify: ldo=%d must be >= %d and a multiple of 8", ldo, K);
   auto* o = reinterpret_cast<__nv_bfloat16*>(out);
   const long long rows = static_cast<long long>(B) * G * G;
+  ProfScope prof(PROF_ROWOPS, static_cast<double>(B) * 3 * R * R * 4.0 + static_cast<double>(rows) * ldo * 2.0, stream);
   if (ldo > K) {
     zero_pad_cols_kernel<<<grid_for(rows * (ldo - K), 256), 256, 0, stream>>>(o, rows, K, ldo);
   }

@@ -3,6 +3,8 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -22,6 +24,63 @@ const char* last_error() { return g_last_error; }
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------
+// Optional per-kernel-class device timing (bench.py's roofline leg): when enabled, every launcher
+// brackets its launch with two CUDA events on the launching stream; summary() synchronises and
+// accumulates elapsed time, algorithmic work and launch counts per class.
+// ---------------------------------------------------------------------------
+namespace {
+struct ProfRec {
+  cudaEvent_t a, b;
+  int cat;
+  double work;
+};
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+bool profiling() { return g_prof_on; }
+
+void prof_begin(int cat, double work, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{prof_event(), prof_event(), cat, work};
+  cudaEventRecord(r.a, s);
+  g_prof_recs.push_back(r);
+}
+void prof_end(cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().b, s);
+}
+void prof_enable(bool on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+  g_prof_recs.clear();
+  g_prof_on = on;
+}
+int prof_summary(double* ms, double* work, long long* launches, int ncat) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < ncat; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
+  for (auto& r : g_prof_recs) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return 1;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return 1;
+    if (r.cat >= 0 && r.cat < ncat) { ms[r.cat] += t; work[r.cat] += r.work; launches[r.cat] += 1; }
+  }
+  return 0;
+}
 
 int num_sms() {
   static int cached[64] = {0};

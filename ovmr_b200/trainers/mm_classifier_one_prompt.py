@@ -91,6 +91,8 @@ class PromptLearner(nn.Module):
         self.n_ctx = n_ctx
         self.tokenized_prompts = tokenized_prompts.to(device)
         self.eot_index_host = tokenized_prompts.argmax(dim=-1)  # host copy: lets the text tower size its sequences
+        self.eot_index_dev = self.eot_index_host.to(device=device, dtype=torch.int32)
+        self.max_eot = int(self.eot_index_host.max())
         self.name_lens = name_lens
 
         # visual token generator (trainers/...:137-154)
@@ -186,10 +188,11 @@ class CustomCLIP(nn.Module):
         pl = self.prompt_learner
         text = self.text_encoder.engine(self.device)
         vtok = pl.visual_tokens(exemplar_features)
-        eot_host = pl.eot_index_host[exemplar_label.cpu()]
-        mm_idx = (eot_host + pl.n_ctx).to(torch.int32)
+        # read-out indices stay on the device (no host sync in the loop); the sequence length is sized once from
+        # the longest class prompt
+        mm_idx = pl.eot_index_dev[exemplar_label.long()] + pl.n_ctx
         v_idx = torch.full_like(mm_idx, 1 + pl.n_ctx)
-        mm = text.encode_spliced(pl.prompt_tokens, exemplar_label, vtok, mm_idx, int(mm_idx.max()), normalize=True)
+        mm = text.encode_spliced(pl.prompt_tokens, exemplar_label, vtok, mm_idx, pl.max_eot + pl.n_ctx, normalize=True)
         v = text.encode_spliced(pl.visual_prompt_temp, None, vtok, v_idx, 1 + pl.n_ctx, normalize=True)
         # mean over the (length-1) prompt list + second normalisation (trainers/...:210-211)
         mm = E.segmented_mean(mm.unsqueeze(1), normalize=True)
@@ -198,8 +201,12 @@ class CustomCLIP(nn.Module):
 
     # ------------------------------------------------------------------ classifier generation
     @torch.no_grad()
-    def forward_prompt(self, eval_set_loader):
-        """trainers/...:214-292 — loop over class-contiguous exemplar batches, F1-driven fusion weights, artefacts."""
+    def forward_prompt(self, eval_set_loader, shard=None):
+        """trainers/...:214-292 — loop over class-contiguous exemplar batches, F1-driven fusion weights, artefacts.
+
+        Multi-GPU (ovmr_b200.dist.Shard): the loader yields only this rank's contiguous class range; classifier
+        rows and the F1 count histograms are all-gathered so every rank ends with identical full classifiers and
+        fusion weights."""
         n_cls = len(self.tokenized_prompts)
         e = self.image_encoder.output_dim
         s = self.test_num_ins
@@ -226,16 +233,29 @@ class CustomCLIP(nn.Module):
             self.visual_classifer[exemplar_label] = v
             self.inference_text_initialized[exemplar_label] = 1
             self.visual_tokens[exemplar_label] = vtok
+        lo, hi = 0, n_cls
+        if shard is not None and shard.world > 1:
+            from .. import dist as D
+            lo, hi = shard.lo, shard.hi
+            self.mm_classifier = D.all_gather_rows(self.mm_classifier[lo:hi].contiguous(), n_cls)
+            self.visual_classifer = D.all_gather_rows(self.visual_classifer[lo:hi].contiguous(), n_cls)
+            self.visual_tokens = D.all_gather_rows(self.visual_tokens[lo:hi].contiguous(), n_cls)
+            self.inference_text_initialized = D.all_gather_rows(self.inference_text_initialized[lo:hi].contiguous(),
+                                                                n_cls)
         assert self.inference_text_initialized.bool().all()
 
-        eval_labels = torch.arange(n_cls, device=dev).reshape(-1, 1).repeat(1, s).flatten(0, 1)
+        # exemplar self-classification (this rank's classes only when sharded) -> global F1 counts
+        eval_labels = torch.arange(lo, hi, device=dev).reshape(-1, 1).repeat(1, s).flatten(0, 1)
         bank = E.ClassifierBank([self.mm_classifier, self.visual_classifer, self.zero_shot_classifier])
-        counts, preds = E.exemplar_counts(bank, self.eval_feat4cls.view(n_cls * s, e), eval_labels, self._scale())
+        counts, preds = E.exemplar_counts(bank, self.eval_feat4cls[lo:hi].reshape((hi - lo) * s, e), eval_labels,
+                                          self._scale())
+        if shard is not None and shard.world > 1:
+            counts = D.all_gather_sum(counts)
         self.fusion_weight, self.exemplar_f1 = E.fusion_weights_from_counts(counts, 3, n_cls, float(self.cfg.EVAL_TAU))
         self.exemplar_preds = preds
         self._banks = {}
         out_dir = getattr(self.cfg, "OUTPUT_DIR", None)
-        if out_dir:
+        if out_dir and (shard is None or shard.rank == 0):
             os.makedirs(out_dir, exist_ok=True)
             torch.save({"text_classifier": self.zero_shot_classifier.float().cpu(),
                         "vision_classifier": self.visual_classifer.float().cpu(),

@@ -1,0 +1,123 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ovmr_b200.h declares; host-side logic
+(config, sharding, loaders, error behaviour) — no compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from tests.helpers import O, ROOT
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ovmr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ovmr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ovmr_b200 import _lib as L
+    lib = L.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ovmr_b200.h but not exported"
+    assert sorted(L.SIGNATURES) == declared, "ctypes SIGNATURES out of sync with the header"
+    assert lib.ovmr_abi_version() == 1
+    assert isinstance(lib.ovmr_last_error(), bytes)
+
+
+def test_abi_struct_layout_matches_header():
+    from ovmr_b200 import _lib as L
+    p = ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(L.BlockWeights) == 12 * p
+    assert ctypes.sizeof(L.Transformer) == 4 * 4 + p
+    assert L.Vit.transformer.offset == 5 * 4 + 4 + 8 * p  # 5 ints, padding, 8 pointers
+    assert L.Text.transformer.offset == 3 * 4 + 4 + 4 * p
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point must fail loudly (never fall back to torch / the oracle)."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ovmr_b200 import _lib as L
+    from ovmr_b200.clip.model import CLIP
+    with pytest.raises(L.OvmrNativeError):
+        L.lib()
+    m = CLIP(*O.CLIP_CONFIGS["tiny"]).eval()
+    with pytest.raises(L.OvmrNativeError):
+        m.encode_image(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(L.OvmrNativeError):
+        m.encode_text(torch.zeros(1, 77, dtype=torch.long))
+    with pytest.raises(L.OvmrNativeError):
+        m.ln_final(torch.zeros(2, 128))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ovmr_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("Oracle", ""), f"{f} references the oracle"
+
+
+def test_state_dict_contract_and_arch_inference():
+    from ovmr_b200.clip.model import CLIP, _arch_from_state_dict, build_model, build_model_fp32
+    cfg = O.CLIP_CONFIGS["tiny"]
+    sd = O.init_clip_state(cfg, seed=0)
+    m = CLIP(*cfg)
+    assert set(m.state_dict()) == set(sd)
+    for k, v in m.state_dict().items():
+        assert v.shape == sd[k].shape, k
+    assert _arch_from_state_dict(sd) == cfg
+    m16 = build_model(sd)
+    assert m16.dtype == torch.float16 and not m16.training        # clip/model.py:899-936 converts to fp16
+    assert build_model_fp32(sd).dtype == torch.float32
+    assert _arch_from_state_dict(O.init_clip_state((64 * 2, 32, 1, 128, 16, 77, 49408, 128, 2, 1))) == \
+        (128, 32, 1, 128, 16, 77, 49408, 128, 2, 1)
+    with pytest.raises(NotImplementedError):
+        CLIP(1024, 224, (3, 4, 6, 3), 64, None, 77, 49408, 512, 8, 12)   # ModifiedResNet: out of scope
+
+
+def test_clip_load_and_tokenize_errors(tmp_path):
+    from ovmr_b200 import clip
+    assert "ViT-B/16" in clip.available_models() and "ViT-L/14@336px" in clip.available_models()
+    assert len(clip.available_models()) == 8
+    with pytest.raises(RuntimeError):
+        clip.load("no-such-model")
+    with pytest.raises(RuntimeError):
+        clip.tokenize("word " * 100)
+    t = clip.tokenize("word " * 100, truncate=True)
+    assert t.shape == (1, 77) and int(t[0, -1]) == 49407
+    assert clip.tokenize(["a", "b c"]).dtype == torch.long
+    # offline entry: a state_dict file
+    path = tmp_path / "tiny.pt"
+    torch.save(O.init_clip_state(O.CLIP_CONFIGS["tiny"]), path)
+    with pytest.warns(UserWarning):
+        model, preprocess = clip.load(str(path), device="cpu")
+    assert model.visual.input_resolution == 64 and model.dtype == torch.float32 and callable(preprocess)
+
+
+def test_precision_policy(monkeypatch):
+    from ovmr_b200 import config
+    p = config.Precision("mixed")
+    assert (p.vision_fp16, p.text_fp16) == (False, True)
+    assert (config.Precision("bf16").vision_fp16, config.Precision("bf16").text_fp16) == (False, False)
+    assert (config.Precision("fp16").vision_fp16, config.Precision("fp16").text_fp16) == (True, True)
+    with pytest.raises(ValueError):
+        config.Precision("int8")
+    cfg = config.make_cfg(shots=4)
+    assert cfg.DATASET.NUM_SHOTS == 4 and cfg.TRAINER.COCOOP.N_CTX == 2 and cfg.EVAL_MODE == "fusion"
+
+
+def test_shard_ranges_partition_exactly():
+    from ovmr_b200.dist import shard_range
+    for n in (0, 1, 7, 1000, 21841, 50000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,123 @@
+"""CPU: the oracle restatement against the golden vectors minted from the reference's own code
+(oracle/gen_golden.py) — this is what pins the oracle on machines without /root/reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import GOLDEN, O
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+
+
+@pytest.mark.parametrize("name", ["tiny_c6s3", "vitb16_cfg1"])
+def test_weight_construction_is_bit_identical_to_reference(name):
+    g = _load(name)
+    cfg = tuple(int(v) for v in g["clip_cfg"])
+    sd = O.init_clip_state(cfg, seed=0)
+    pl = O.init_prompt_learner_state(cfg[0], n_ctx=int(g["n_ctx"]), seed=1)
+    digest = O.state_digest({**sd, **{"prompt_learner." + k: v for k, v in pl.items()}})
+    keys = [str(k) for k in g["digest_keys"]]
+    assert sorted(digest) == keys
+    got = np.array([digest[k] for k in keys])
+    assert np.array_equal(got, g["digest_vals"]), "oracle weights differ from the reference's state_dict"
+    # every weight is bf16-representable, so the bf16 CUDA path and the fp32 reference share the same values
+    for v in sd.values():
+        assert torch.equal(v, v.bfloat16().float())
+
+
+@pytest.mark.parametrize("name", ["tiny_c6s3", "tiny_c6s3_structured"])
+def test_oracle_matches_reference_outputs_tiny(name):
+    g = _load(name)
+    cfg = tuple(int(v) for v in g["clip_cfg"])
+    C, S, Q, res = int(g["C"]), int(g["S"]), int(g["Q"]), int(g["res"])
+    sd = O.init_clip_state(cfg, seed=0)
+    pl = O.init_prompt_learner_state(cfg[0], n_ctx=int(g["n_ctx"]), seed=1)
+    labels = torch.arange(C).repeat_interleave(S)
+    structured = bool(int(g["structured"]))
+    ex = O.synth_images(C * S, res, seed=1, structured_classes=labels if structured else None)
+    qs = O.synth_images(Q, res, seed=1001, structured_classes=(torch.arange(Q) % C) if structured else None)
+    tok = torch.from_numpy(g["tokenized_prompts"]).long()
+    vt = torch.from_numpy(g["visual_template_tokens"]).long()
+    with torch.no_grad():
+        t_cls = O.zero_shot_classifier(sd, tok)
+        gen = O.forward_prompt(sd, pl, tok, vt, t_cls, [(ex, labels)], S, tau=float(g["tau"]))
+        qf = O.encode_image(sd, qs)
+        probs = O.classify(sd["logit_scale"].exp(), O.l2n(qf), gen, "fusion")
+    tol = dict(atol=5e-6, rtol=0)
+    for k in ("text_classifier", "mm_classifier", "vision_classifier"):
+        assert np.allclose(gen[k].numpy(), g[k], **tol), k
+    assert np.allclose(gen["visual_tokens"].numpy(), g["visual_tokens"], atol=2e-5)
+    assert np.allclose(qf.numpy(), g["query_features"], atol=2e-5)
+    assert np.allclose(gen["fusion_weight"].numpy(), g["fusion_weight"], atol=1e-6)
+    assert np.allclose(probs.numpy(), g["fused_probs"], atol=2e-6)
+    assert np.array_equal(probs.argmax(1).numpy(), g["argmax"])
+    assert np.array_equal(gen["exemplar_preds"].numpy(), g["exemplar_preds"])
+    # the other eval modes are plain softmaxes that sum to one; fusion rows need not
+    for mode in ("text", "vision", "multimodal"):
+        p = O.classify(sd["logit_scale"].exp(), O.l2n(qf), gen, mode)
+        assert torch.allclose(p.sum(1), torch.ones(Q), atol=1e-5)
+
+
+def test_oracle_matches_reference_outputs_vitb16_cfg1():
+    """BASELINE config 1 (the reference's own CPU-runnable case), bounded to the classifiers + 8 queries."""
+    g = _load("vitb16_cfg1")
+    cfg = tuple(int(v) for v in g["clip_cfg"])
+    C, S, res = int(g["C"]), int(g["S"]), int(g["res"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.init_clip_state(cfg, seed=0)
+    pl = O.init_prompt_learner_state(cfg[0], n_ctx=2, seed=1)
+    labels = torch.arange(C).repeat_interleave(S)
+    ex = O.synth_images(C * S, res, seed=1)
+    qs = O.synth_images(8, res, seed=1001)
+    tok = torch.from_numpy(g["tokenized_prompts"]).long()
+    vt = torch.from_numpy(g["visual_template_tokens"]).long()
+    with torch.no_grad():
+        t_cls = O.zero_shot_classifier(sd, tok)
+        gen = O.forward_prompt(sd, pl, tok, vt, t_cls, [(ex, labels)], S, tau=10.0)
+        qf = O.encode_image(sd, qs)
+        probs = O.classify(sd["logit_scale"].exp(), O.l2n(qf), gen, "fusion")
+    for k in ("text_classifier", "mm_classifier", "vision_classifier"):
+        assert np.allclose(gen[k].numpy(), g[k], atol=5e-6), k
+    assert np.allclose(gen["fusion_weight"].numpy(), g["fusion_weight"], atol=1e-6)
+    assert np.allclose(qf.numpy(), g["query_features"][:8], atol=3e-5)
+    assert np.allclose(probs.numpy(), g["fused_probs"][:8], atol=2e-6)
+    deltas = json.loads(str(g["oracle_vs_reference"]))
+    assert deltas["argmax_agree"] == 1.0 and deltas["fused_probs"] < 1e-5
+
+
+def test_tokenizer_matches_reference_goldens():
+    from ovmr_b200.clip import tokenize
+    g = _load("tokenizer")
+    strings = [str(s) for s in g["strings"]]
+    toks = tokenize(strings, truncate=True).numpy()
+    lens = (toks != 0).sum(1)
+    assert np.array_equal(lens, g["lens"])
+    assert np.array_equal(np.concatenate([t[:n] for t, n in zip(toks, lens)]), g["flat"])
+    # "a class 0." -> [49406, 320, 1874, 271, 269, 49407, 0...], EOT index 5
+    t = tokenize("a class 0.")[0]
+    assert t[:6].tolist() == [49406, 320, 1874, 271, 269, 49407] and int(t.argmax()) == 5
+
+
+def test_f1_restatement_matches_sklearn():
+    """torcheval is not vendored by the reference ("parity unpinned" there); cross-check with sklearn,
+    which the reference's own evaluator uses for F1 (dassl/evaluation/evaluator.py:100-105)."""
+    from sklearn.metrics import f1_score
+    g = torch.Generator().manual_seed(0)
+    for C, n in [(5, 40), (37, 185), (10, 10)]:
+        y = torch.randint(0, C, (n,), generator=g)
+        p = torch.where(torch.rand(n, generator=g) < 0.6, y, torch.randint(0, C, (n,), generator=g))
+        ref = f1_score(y.numpy(), p.numpy(), labels=list(range(C)), average=None, zero_division=0)
+        assert np.allclose(O.multiclass_f1(p, y, C).numpy(), ref, atol=1e-6)
+
+
+def test_topk_ties_resolve_to_lowest_index():
+    p = torch.tensor([[0.2, 0.5, 0.5, 0.1], [0.3, 0.3, 0.3, 0.3]])
+    i1, _ = O.topk(p, 1)
+    assert i1[:, 0].tolist() == [1, 0]
+    i2, v2 = O.topk(p, 3)
+    assert i2.tolist() == [[1, 2, 0], [0, 1, 2]]
