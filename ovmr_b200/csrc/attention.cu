@@ -13,6 +13,9 @@
 // accumulate), softmax is the online (flash) form in fp32 with exp2.
 #include "attention.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace ovmr {
@@ -215,6 +218,13 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 int attention(const void* qkv, void* out, int n_seq, int L, int D, int heads, int causal, int fp16, cudaStream_t stream) {
   OVMR_REQUIRE(n_seq > 0 && L > 0 && heads > 0 && D == heads * HD, "attention: need D == heads*64 (D=%d heads=%d L=%d)", D,
                heads, L);
+  // shape specialisation: the vision towers' sequence lengths run on the tcgen05 kernel; short sequences (text,
+  // aggregator) and L > 256 (ViT-L/14) on the streaming mma.sync kernel below.  OVMR_ATTN_IMPL=legacy|tc overrides.
+  static const int impl = [] {
+    const char* e = getenv("OVMR_ATTN_IMPL");
+    return e == nullptr ? 0 : (!strcmp(e, "legacy") ? 1 : (!strcmp(e, "tc") ? 2 : 0));
+  }();
+  if (L <= 256 && (impl == 2 || (impl == 0 && L > 64))) return attention_tc(qkv, out, n_seq, L, D, heads, causal, fp16, stream);
   OVMR_REQUIRE(n_seq <= 65535 && heads <= 65535, "attention: grid limits (n_seq=%d)", n_seq);
   const int nkb = (L + KB - 1) / KB;
   const size_t smem = (static_cast<size_t>(2) * nkb * KB + QT) * PITCH * 2;

@@ -9,4 +9,7 @@ namespace ovmr {
 // fp16 != 0: qkv/out are IEEE fp16 instead of bf16.
 int attention(const void* qkv, void* out, int n_seq, int L, int D, int heads, int causal, int fp16, cudaStream_t stream);
 
+// tcgen05/TMEM implementation for L <= 256 (attention_tc.cu); `attention` dispatches to it for 64 < L <= 256.
+int attention_tc(const void* qkv, void* out, int n_seq, int L, int D, int heads, int causal, int fp16, cudaStream_t stream);
+
 }  // namespace ovmr

@@ -1,0 +1,278 @@
+// ovmr_b200 — tcgen05/TMEM fused softmax attention for sequences of 64 < L <= 256 tokens
+// (the vision towers: L = 197 for ViT-B/16, 50 for B/32 is served by the mma.sync kernel).
+//
+// Same arithmetic as attention.cu (nn.MultiheadAttention core, clip/model.py:184-189) but on the 5th-gen
+// tensor cores.  One persistent CTA per SM walks (sequence, head) pairs; for each 128-query tile:
+//
+//   S = Q K^T      tcgen05.mma  M=128, N=Lpad, K=64   A,B from smem (TMA, 128B swizzle) -> TMEM fp32
+//   P = softmax    128 threads, one query row each: tcgen05.ld S, masked max, exp2, row sum,
+//                  P packed to 16-bit and written BACK INTO TMEM over S (tcgen05.st)
+//   O = P V        tcgen05.mma  M=128, N=64, K=Lpad   A = P from TMEM, B = V from smem (MN-major)
+//   out = O / sum  tcgen05.ld O, scale, 128 B per row to global
+//
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 UMMA issuer, warp 2 TMEM allocator,
+// warps 4-7 / 8-11 two softmax groups that ping-pong over consecutive query tiles (tile t uses
+// TMEM region t&1), so the exp-bound softmax of one tile overlaps the MMAs of the next.
+// TMEM map per region (256 columns): S [0,Lpad) fp32; P [0,Lpad/2) packed 16-bit (aliases S, written
+// only after the whole S row has been read twice); O [128,192) fp32 (S columns that are dead by then).
+#include "attention.cuh"
+#include "common.cuh"
+
+namespace ovmr {
+
+namespace {
+
+constexpr int ATC_THREADS = 384;
+constexpr int QTILE = 128;
+constexpr uint32_t Q_BYTES = QTILE * 128;  // 128 rows x 64 x 2 B
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    void* __restrict__ out_, int n_seq, int L, int Lpad, int D, int heads, int causal,
+                    float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw_addr);
+  const uint32_t kv_bytes = static_cast<uint32_t>(Lpad) * 128u;        // one K or V tile
+  const uint32_t kv_stride = (kv_bytes + 1023u) & ~1023u;
+  const uint32_t sQ = base;                                            // 2 stages
+  const uint32_t sK = sQ + 2 * Q_BYTES;                                // 2 stages
+  const uint32_t sV = sK + 2 * kv_stride;                              // 2 stages
+  const uint32_t bars = sV + 2 * kv_stride;
+  // barrier slots (8 B each)
+  auto kv_full = [&](uint32_t s) { return bars + 8u * (0 + s); };
+  auto kv_empty = [&](uint32_t s) { return bars + 8u * (2 + s); };
+  auto q_full = [&](uint32_t s) { return bars + 8u * (4 + s); };
+  auto q_empty = [&](uint32_t s) { return bars + 8u * (6 + s); };
+  auto s_full = [&](uint32_t s) { return bars + 8u * (8 + s); };
+  auto p_full = [&](uint32_t s) { return bars + 8u * (10 + s); };
+  auto o_full = [&](uint32_t s) { return bars + 8u * (12 + s); };
+  auto r_free = [&](uint32_t s) { return bars + 8u * (14 + s); };
+  const uint32_t tmem_slot = bars + 8u * 16;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_work = n_seq * heads;
+  const int nqt = (L + QTILE - 1) / QTILE;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
+      mbar_init(s_full(s), 1);
+      mbar_init(p_full(s), 128);
+      mbar_init(o_full(s), 1);
+      mbar_init(r_free(s), 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      uint32_t t = 0, wi = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
+        const int seq = w / heads, h = w % heads;
+        const uint32_t ks = wi & 1u, kn = wi >> 1;
+        mbar_wait(kv_empty(ks), (kn & 1u) ^ 1u);
+        mbar_arrive_expect_tx(kv_full(ks), 2 * kv_bytes);
+        tma_load_2d(sK + ks * kv_stride, &tmKV, kv_full(ks), D + h * 64, seq * L);
+        tma_load_2d(sV + ks * kv_stride, &tmKV, kv_full(ks), 2 * D + h * 64, seq * L);
+        for (int j = 0; j < nqt; ++j, ++t) {
+          const uint32_t qs = t & 1u, qn = t >> 1;
+          mbar_wait(q_empty(qs), (qn & 1u) ^ 1u);
+          mbar_arrive_expect_tx(q_full(qs), Q_BYTES);
+          tma_load_2d(sQ + qs * Q_BYTES, &tmQ, q_full(qs), h * 64, seq * L + j * QTILE);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== UMMA issuer =====================
+      const uint32_t idesc_s = umma_idesc_16b_f32(QTILE, Lpad, FP16 ? 1 : 0);
+      const uint32_t idesc_o = umma_idesc_16b_f32_bmn(QTILE, 64, FP16 ? 1 : 0);
+      const int ksteps = Lpad / 16;
+      // PV of the previous tile is issued AFTER S of the current one (software pipeline)
+      bool have_prev = false;
+      uint32_t prev_t = 0, prev_ks = 0;
+      bool prev_last = false;
+      auto issue_pv = [&](uint32_t t, uint32_t ks, bool last_of_work) {
+        const uint32_t r = t & 1u, n = t >> 1;
+        mbar_wait(p_full(r), n & 1u);
+        tc_fence_after();
+        const uint32_t region = tmem_base + r * 256u;
+        const uint64_t v_desc = umma_desc_mn_sw128(sV + ks * kv_stride, kv_bytes);
+        for (int kk = 0; kk < ksteps; ++kk) {
+          // 16 keys per step: 8 packed TMEM columns of P, 16 rows (2048 B) of V
+          umma_16b_ts(region + 128u, region + 8u * kk, v_desc + 128u * kk, idesc_o, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(o_full(r));
+        if (last_of_work) umma_commit(kv_empty(ks));
+      };
+      uint32_t t = 0, wi = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
+        const uint32_t ks = wi & 1u, kn = wi >> 1;
+        for (int j = 0; j < nqt; ++j, ++t) {
+          const uint32_t r = t & 1u, n = t >> 1, qs = t & 1u;
+          mbar_wait(r_free(r), (n & 1u) ^ 1u);   // softmax group has drained O of the tile 2 steps back
+          mbar_wait(q_full(qs), n & 1u);
+          if (j == 0) mbar_wait(kv_full(ks), kn & 1u);
+          tc_fence_after();
+          const uint64_t q_desc = umma_desc_k_sw128(sQ + qs * Q_BYTES);
+          const uint64_t k_desc = umma_desc_k_sw128(sK + ks * kv_stride);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tmem_base + r * 256u, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(s_full(r));
+          umma_commit(q_empty(qs));
+          if (have_prev) issue_pv(prev_t, prev_ks, prev_last);
+          have_prev = true;
+          prev_t = t;
+          prev_ks = ks;
+          prev_last = (j == nqt - 1);
+        }
+      }
+      if (have_prev) issue_pv(prev_t, prev_ks, prev_last);
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax + output (two groups of 4 warps) =====================
+    const uint32_t grp = (warp - 4) >> 2;       // handles tiles with (t & 1) == grp
+    const uint32_t quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;        // query row inside the tile
+    const int nchunk = Lpad / 16;
+    uint32_t t = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int seq = w / heads, h = w % heads;
+      for (int j = 0; j < nqt; ++j, ++t) {
+        if ((t & 1u) != grp) continue;
+        const uint32_t r = grp, n = t >> 1;
+        const int q_idx = j * QTILE + row;
+        const int kmax = causal ? min(L - 1, q_idx) : L - 1;   // last visible key of this row
+        mbar_wait(s_full(r), n & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (quarter * 32u << 16) + r * 256u;
+        // ---- pass 1: masked row max
+        float m = -INFINITY;
+        for (int c = 0; c < nchunk; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + 16 * c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (16 * c + e <= kmax) m = fmaxf(m, __uint_as_float(v[e]));
+        }
+        const float ms = (m == -INFINITY) ? 0.f : m * scale_log2e;
+        // ---- pass 2: exp2, row sum, pack, write P over S
+        float sum = 0.f;
+        for (int c = 0; c < nchunk; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + 16 * c, v);
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const float p0 = (16 * c + e <= kmax) ? ex2f(fmaf(__uint_as_float(v[e]), scale_log2e, -ms)) : 0.f;
+            const float p1 = (16 * c + e + 1 <= kmax) ? ex2f(fmaf(__uint_as_float(v[e + 1]), scale_log2e, -ms)) : 0.f;
+            sum += p0 + p1;
+            pk[e >> 1] = FP16 ? pack_f16x2(p0, p1) : pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x32b_x8(taddr + 8 * c, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full(r));
+        // ---- O = P V is ready: normalise and store this row (64 x 16-bit = 128 B)
+        mbar_wait(o_full(r), n & 1u);
+        tc_fence_after();
+        const float inv = 1.0f / sum;
+        uint16_t* orow = reinterpret_cast<uint16_t*>(out_) + (static_cast<long long>(seq) * L + q_idx) * D + h * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + 128 + 16 * c, v);
+          tmem_ld_wait();
+          if (c == 3) {
+            tc_fence_before();
+            mbar_arrive(r_free(r));   // region reusable: everything of this tile is in registers
+          }
+          if (q_idx < L) {
+            uint4 o0, o1;
+            auto pk2 = [&](int e) {
+              const float a = __uint_as_float(v[e]) * inv, b = __uint_as_float(v[e + 1]) * inv;
+              return FP16 ? pack_f16x2(a, b) : pack_bf16x2(a, b);
+            };
+            o0.x = pk2(0); o0.y = pk2(2); o0.z = pk2(4); o0.w = pk2(6);
+            o1.x = pk2(8); o1.y = pk2(10); o1.z = pk2(12); o1.w = pk2(14);
+            reinterpret_cast<uint4*>(orow + 16 * c)[0] = o0;
+            reinterpret_cast<uint4*>(orow + 16 * c)[1] = o1;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int attention_tc(const void* qkv, void* out, int n_seq, int L, int D, int heads, int causal, int fp16,
+                 cudaStream_t stream) {
+  OVMR_REQUIRE(L > 0 && L <= 256 && D == heads * 64, "attention_tc: need L <= 256 and D == heads*64 (L=%d D=%d)", L, D);
+  const int Lpad = (L + 15) / 16 * 16;
+  const long long rows = static_cast<long long>(n_seq) * L;
+  CUtensorMap tmQ, tmKV;
+  int rc = make_tmap_16b(&tmQ, qkv, rows, 3LL * D, 3LL * D, QTILE);
+  if (rc) return rc;
+  rc = make_tmap_16b(&tmKV, qkv, rows, 3LL * D, 3LL * D, Lpad);
+  if (rc) return rc;
+  const uint32_t kv_stride = (static_cast<uint32_t>(Lpad) * 128u + 1023u) & ~1023u;
+  const size_t smem = 2 * Q_BYTES + 4 * static_cast<size_t>(kv_stride) + 8 * 17 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    const int max_smem = 2 * Q_BYTES + 4 * 32768 + 8 * 17 + 16 + 1024;
+    OVMR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    OVMR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    configured = true;
+  }
+  const int n_work = n_seq * heads;
+  const int grid = n_work < num_sms() ? n_work : num_sms();
+  const float scale_log2e = 0.125f * 1.4426950408889634f;
+  ProfScope prof(PROF_ATTENTION, 4.0 * n_seq * heads * static_cast<double>(L) * L * 64 * (causal ? 0.5 : 1.0), stream);
+  if (fp16)
+    attention_tc_kernel<true><<<grid, ATC_THREADS, smem, stream>>>(tmQ, tmKV, out, n_seq, L, Lpad, D, heads, causal, scale_log2e);
+  else
+    attention_tc_kernel<false><<<grid, ATC_THREADS, smem, stream>>>(tmQ, tmKV, out, n_seq, L, Lpad, D, heads, causal, scale_log2e);
+  OVMR_CHECK_CUDA(cudaGetLastError());
+  count_launches(1);
+  return 0;
+}
+
+}  // namespace ovmr

@@ -21,6 +21,8 @@ namespace ovmr {
 void set_last_error(const char* fmt, ...);
 int num_sms();
 void count_launches(int n);  // bookkeeping for ovmr_launch_count()
+// TMA descriptor of a 16-bit row-major matrix, boxes of box_rows x 64 elements, 128-byte swizzle (zero OOB fill)
+int make_tmap_16b(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
 
 // kernel classes for the optional device-side timing (see runtime.cu)
 enum ProfCat { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_ROWOPS = 3, PROF_HEAD = 4, PROF_NCAT = 5 };
@@ -173,8 +175,73 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 
 // ----------------------------------------------------------------------------
+// Thread-block clusters / CTA pairs
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `cta` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+// CTA-pair TMA load: data lands in THIS CTA's smem, the transaction bytes are signalled on the
+// LEADER CTA's mbarrier (peer bit of the shared::cluster address cleared).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar,
+                                                 int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// CTA-pair UMMA: M = 256 across the two CTAs' TMEM, issued by the leader CTA only.
+__device__ __forceinline__ void umma_16b_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the pair's MMAs, arriving on the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_pair_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
                "r"(ncols)
@@ -226,6 +293,39 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
       : "r"(taddr)
       : "memory");
 }
+// TMEM -> registers: 32 lanes x 16 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// registers -> TMEM: 32 lanes x 8 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+               "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (16-bit, two K elements per 32-bit column) lives in TMEM.
+__device__ __forceinline__ void umma_16b_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -243,6 +343,17 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;           // SWIZZLE_128B
   return d;
 }
+// MN-major operand tile (rows = K index, 64 contiguous MN elements = 128 B per row), 128-byte swizzle:
+// SBO = 1024 B between 8-row K groups, LBO = byte distance between 64-element MN atoms.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // UMMA instruction descriptor, kind::f16: A/B both bf16 (fp16 == 0) or both fp16, K-major, fp32 accumulate.
 __host__ __device__ constexpr uint32_t umma_idesc_16b_f32(int M, int N, int fp16) {
   return (1u << 4)                               // D format  = f32
@@ -250,6 +361,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_16b_f32(int M, int N, int fp16
          | ((fp16 ? 0u : 1u) << 10)              // B format
          | (static_cast<uint32_t>(N >> 3) << 17) // N / 8
          | (static_cast<uint32_t>(M >> 4) << 24);// M / 16
+}
+// same, with the B operand MN-major (bit 16)
+__host__ __device__ constexpr uint32_t umma_idesc_16b_f32_bmn(int M, int N, int fp16) {
+  return umma_idesc_16b_f32(M, N, fp16) | (1u << 16);
 }
 #endif  // __CUDACC__
 

@@ -30,7 +30,7 @@ struct GemmEpilogue {
 
 // A: 16-bit [M,K] leading dim lda (elements); B: 16-bit [N,K] leading dim ldb (format: ep.fp16).
 // Requirements: K % 8 == 0, N % 8 == 0, lda/ldb % 8 == 0, 16-byte aligned bases.
-// force_block_n: 0 = heuristic, else 128 or 256.
+// force_block_n: 0 = heuristic, 128 / 256 = 1-CTA kernel with that tile width, 512 = CTA-pair (2-SM) kernel.
 int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                  const GemmEpilogue& ep, cudaStream_t stream, int force_block_n = 0);
 

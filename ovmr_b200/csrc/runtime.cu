@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <cudaTypedefs.h>
+
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -81,6 +83,47 @@ int prof_summary(double* ms, double* work, long long* launches, int ncat) {
   }
   return 0;
 }
+
+namespace {
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+  });
+  return fn;
+}
+
+}  // namespace
+
+// 16-bit row-major [rows, cols] (cols contiguous, leading dim ld) -> tiles of box_rows x 64, 128B swizzle
+int make_tmap_16b(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
+                   int box_rows) {
+  auto enc = tensor_map_encoder();
+  if (!enc) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    return OVMR_ERR_INVALID;
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d) base=%p rows=%lld cols=%lld ld=%lld box_rows=%d",
+                   (int)r, base, rows, cols, ld, box_rows);
+    return OVMR_ERR_INVALID;
+  }
+  return 0;
+}
+
 
 int num_sms() {
   static int cached[64] = {0};

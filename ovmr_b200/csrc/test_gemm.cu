@@ -179,6 +179,14 @@ int main(int argc, char** argv) {
       {"heuristic",     1576,   512,  512,  1,  0,  1,  0,  0,   0, 1.0f, 0},
   };
   if (!quick) {
+    cases.push_back({"pair-small", 512, 512, 256, 0, 0, 1, 0, 0, 512, 1.0f, 0});
+    cases.push_back({"pair-tails", 1000, 3000, 1536, 0, 0, 1, 1, 0, 512, 1.0f, 0});
+    cases.push_back({"pair-gelu", 5000, 3072, 768, 1, 1, 1, 0, 0, 512, 1.0f, 0});
+    cases.push_back({"pair-patch", 392, 768, 768, 0, 0, 0, 1, 196, 512, 1.0f, 0});
+    cases.push_back({"vit-qkv-pair", 50432, 2304, 768, 1, 0, 1, 0, 0, 512, 1.0f, 10});
+    cases.push_back({"vit-out-pair", 50432, 768, 768, 0, 0, 1, 1, 0, 512, 1.0f, 10});
+    cases.push_back({"vit-fc-pair", 50432, 3072, 768, 1, 1, 1, 0, 0, 512, 1.0f, 10});
+    cases.push_back({"vit-proj-pair", 50432, 768, 3072, 0, 0, 1, 1, 0, 512, 1.0f, 10});
     cases.push_back({"vit-qkv-256", 50432, 2304, 768, 1, 0, 1, 0, 0, 256, 1.0f, 10});
     cases.push_back({"vit-qkv-128", 50432, 2304, 768, 1, 0, 1, 0, 0, 128, 1.0f, 10});
     cases.push_back({"vit-out", 50432, 768, 768, 0, 0, 1, 1, 0, 256, 1.0f, 10});

@@ -26,7 +26,8 @@ def _bf16r(x):
 
 
 @pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (200, 384, 768, 0), (1000, 768, 3072, 256),
-                                      (333, 3000, 1536, 0), (50, 512, 512, 128), (4097, 2304, 768, 256)])
+                                      (333, 3000, 1536, 0), (50, 512, 512, 128), (4097, 2304, 768, 256),
+                                      (4097, 2304, 768, 512), (300, 3000, 512, 512), (20000, 768, 768, 0)])
 @pytest.mark.parametrize("mode", ["bf16_bias", "bf16_gelu", "f32_resid", "fp16_gelu", "fp16_f32_resid"])
 def test_gemm(M, N, K, bn, mode):
     L, lib = _lib()
@@ -115,7 +116,9 @@ def test_layernorm_gather_and_chain():
 
 
 @pytest.mark.parametrize("n_seq,Lq,heads,causal", [(3, 197, 12, 0), (5, 77, 8, 1), (4, 6, 2, 0), (2, 18, 8, 0),
-                                                   (2, 8, 8, 1), (1, 577, 16, 0), (2, 64, 2, 1), (2, 65, 2, 1)])
+                                                   (2, 8, 8, 1), (1, 577, 16, 0), (2, 64, 2, 1), (2, 65, 2, 1),
+                                                   (3, 128, 2, 0), (2, 129, 4, 1), (2, 256, 2, 0), (40, 197, 12, 0),
+                                                   (1, 250, 1, 1)])
 @pytest.mark.parametrize("fp16", [0, 1])
 def test_attention(n_seq, Lq, heads, causal, fp16):
     L, lib = _lib()
