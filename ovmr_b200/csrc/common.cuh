@@ -23,6 +23,9 @@ int num_sms();
 void count_launches(int n);  // bookkeeping for ovmr_launch_count()
 // TMA descriptor of a 16-bit row-major matrix, boxes of box_rows x 64 elements, 128-byte swizzle (zero OOB fill)
 int make_tmap_16b(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
+// general form: element size 2 or 4 bytes, box inner extent must be 128 bytes
+int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, long long rows, long long cols, long long ld,
+                 int box_rows, int box_cols);
 
 // kernel classes for the optional device-side timing (see runtime.cu)
 enum ProfCat { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_ROWOPS = 3, PROF_HEAD = 4, PROF_NCAT = 5 };
@@ -150,6 +153,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// L2 prefetch of one tensor-map box (no shared memory involved)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
 }
 // 2-D tiled store shared -> global (bulk async group).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int32_t c0,
@@ -324,6 +333,20 @@ __device__ __forceinline__ void umma_16b_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
       "}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// pointer form (v must resolve to registers after unrolling)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {

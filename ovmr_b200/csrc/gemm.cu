@@ -7,15 +7,26 @@
 // (clip/model.py:423-426, 827-831) and the cosine-logit head
 // (trainers/mm_classifier_one_prompt.py:263-265, 358-360).
 //
-// Structure (one CTA per SM, 384 threads):
-//   warp 0 / lane 0 : TMA producer   — A[128x64] + B[BLOCK_N x 64] bf16 tiles, 128B swizzle
-//   warp 1 / lane 0 : UMMA issuer    — tcgen05.mma 128 x BLOCK_N x 16, fp32 accum in TMEM
+// Two kernels share the same structure (384 threads):
+//   warp 0 / lane 0 : TMA producer   — A / B 16-bit tiles (128-B swizzle) into an mbarrier ring
+//   warp 1 / lane 0 : UMMA issuer    — tcgen05.mma, fp32 accumulators in TMEM, 2 accumulator stages
 //   warp 2          : TMEM allocator
-//   warps 4..11     : epilogue       — tcgen05.ld -> smem transpose -> bias/QuickGELU/residual
-//                                       -> coalesced global stores
-// Pipelines: smem ring (full/empty mbarriers, TMA <-> UMMA) and a 2-deep TMEM
-// accumulator ring (tmem_full/tmem_empty, UMMA <-> epilogue) so the epilogue of
-// tile i overlaps the main loop of tile i+1.
+//   warps 4..11     : epilogue       — tcgen05.ld -> fused epilogue -> global
+//  * gemm_tn_kernel<BLOCK_N>   one CTA per SM, 128 x BLOCK_N tiles (cta_group::1)
+//  * gemm_tn_pair_kernel       CTA pair of a 2-cluster, 256 x 256 tiles (cta_group::2): each CTA stages its own
+//                              128 A rows and HALF of the B tile, the leader's UMMA (M = 256) reads B from both
+//                              CTAs' shared memory; halves the B traffic through shared memory per SM.
+// The smem ring (full/empty, TMA <-> UMMA) and the TMEM ring (tmem_full/tmem_empty, UMMA <-> epilogue) let the
+// epilogue of tile i overlap the main loop of tile i+1.
+//
+// Epilogue modes (template MODE):
+//   EPI_GENERIC    fp32 out = alpha*acc + bias, act, + fp32 residual, optional patch-row scatter; staged through
+//                  a per-warp smem transpose for coalesced direct stores.  Small / irregular GEMMs.
+//   EPI_16(_GELU)  16-bit out = (QuickGELU)(acc + bias): each warp packs its 32 rows x 64 columns into a
+//                  128B-swizzled smem box and ONE lane issues a TMA store (no per-thread global stores).
+//   EPI_F32_RESID  fp32 out = acc + bias + resid: the residual box (32 rows x 32 cols) is TMA-LOADED into the
+//                  staging buffer one chunk ahead (and L2-prefetched one tile ahead), updated in place by the
+//                  owning threads and TMA-stored.
 #include "gemm.cuh"
 
 #include "common.cuh"
@@ -25,21 +36,12 @@ namespace ovmr {
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom
+constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
+constexpr int GEMM_THREADS = 384;         // 4 control warps + 8 epilogue warps
+constexpr uint32_t BOX_BYTES = 32 * 128;  // one epilogue staging box: 32 rows x 128 B
 
-template <int BLOCK_N>
-struct GemmCfg {
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (256 or 512)
-  static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
-  static constexpr uint32_t STG_BYTES = 8 * 32 * 128;  // per-epilogue-warp 32 x 128 B transpose buffers
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;  // + align slack
-};
+enum EpiMode { EPI_GENERIC = 0, EPI_16 = 1, EPI_16_GELU = 2, EPI_F32_RESID = 3 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
   // x * sigmoid(1.702 x) with sigmoid(y) = 0.5 + 0.5 tanh(y/2): one MUFU op per element
@@ -49,43 +51,150 @@ __device__ __forceinline__ float quick_gelu(float x) {
   return fmaf(hx, t, hx);
 }
 
+// per-warp epilogue bookkeeping
+struct EpiCtx {
+  uint32_t stg;     // this warp's staging boxes (STG_BUFS x 4 KB, 1024-B aligned)
+  uint32_t rbar;    // this warp's two residual-load mbarriers
+  uint32_t n_use;   // staging boxes consumed so far (box k lives in buffer k % STG_BUFS)
+  uint32_t n_load;  // residual loads issued so far (load k -> buffer k % STG_BUFS, barrier k & 1)
+};
 
-// Epilogue of one 128 x BLOCK_N accumulator tile held in this CTA's TMEM (8 warps): tcgen05.ld -> per-warp smem
-// transpose -> alpha/bias/QuickGELU/residual -> coalesced stores.  A warp may only read the TMEM lane quarter
-// (warp % 4); warps w and w+4 share a quarter and split the tile's columns in halves.
-// PAIR: the tmem_empty barrier lives in the leader CTA of the pair (remote arrive).
-template <int BLOCK_N, int OUT_16, bool PAIR>
-__device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int N, int tile_row0, int tile_col0,
-                                              uint32_t tmem_acc, uint32_t tfull, uint32_t tfull_phase,
-                                              uint32_t tempty, uint32_t stg_base, int warp, int lane) {
-  const int ew = warp & 3;
-  const int half = (warp - 4) >> 2;
-  constexpr int HALF_N = BLOCK_N / 2;
-  constexpr int CHUNKS = HALF_N / 32;
-  const uint32_t stg = stg_base + (warp - 4) * 4096;
-  // Coalesced mapping used for all global traffic: lane -> (sub-row lane/8, 16-B column
-  // chunk lane%8); one warp instruction then touches 4 rows x 128 contiguous bytes.
-  const int sub = lane >> 3, cj = lane & 7;
-  const int row0 = tile_row0 + ew * 32;
-  const int ncol0 = tile_col0 + half * HALF_N + 4 * cj;  // + 32*c per chunk
-  // bias for all of this lane's columns, fetched while the main loop is still running
-  float4 bv[CHUNKS];
-#pragma unroll
-  for (int c = 0; c < CHUNKS; ++c) {
-    const int n = ncol0 + 32 * c;
-    bv[c] = (ep.bias && n + 4 <= N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+template <bool PAIR>
+__device__ __forceinline__ void release_accumulator(uint32_t tempty, int lane) {
+  // accumulator fully drained into registers: hand the TMEM stage back to the issuer (one arrive per warp)
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) {
+    if (PAIR) mbar_arrive_remote(tempty, 0);
+    else mbar_arrive(tempty);
   }
-  mbar_wait(tfull, tfull_phase);
-  tc_fence_after();
-  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(ew * 32) << 16) + half * HALF_N;
-  uint32_t v[32];
-  tmem_ld_32x32b_x32(taddr, v);
-#pragma unroll
+}
+
+// ---------------------------------------------------------------------------------------------
+// EPI_16 / EPI_16_GELU: this warp's 32 rows x HALF_N columns, 64 columns (one 128-B box row) at a time.
+// ---------------------------------------------------------------------------------------------
+template <int HALF_N, bool GELU, int STG_BUFS, bool PAIR>
+__device__ __forceinline__ void epilogue_16(const GemmEpilogue& ep, const CUtensorMap* tmC, int N, int row0, int col0,
+                                            uint32_t taddr, uint32_t tempty, EpiCtx& cx, int lane) {
+  constexpr int CHUNKS = HALF_N / 64;
+#pragma unroll 1
   for (int c = 0; c < CHUNKS; ++c) {
-    const int n = ncol0 + 32 * c;  // this lane's 4 output columns
+    const int n0 = col0 + 64 * c;
+    uint32_t v[64];
+    tmem_ld32(taddr + 64 * c, v);
+    tmem_ld32(taddr + 64 * c + 32, v + 32);
+    tmem_ld_wait();
+    if (c == CHUNKS - 1) release_accumulator<PAIR>(tempty, lane);
+    if (n0 >= N) continue;
+    // the staging box is free once the TMA store that last used it has read it
+    const uint32_t buf = cx.stg + (cx.n_use % STG_BUFS) * BOX_BYTES;
+    ++cx.n_use;
+    if (lane == 0) tma_store_wait_read<STG_BUFS - 1>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // 8 columns -> one 16-B chunk
+      float x[8];
+      const int n = n0 + 8 * j;
+      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+      if (ep.bias && n + 8 <= N) {
+        b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+        b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
+      }
+      x[0] = __uint_as_float(v[8 * j + 0]) + b0.x; x[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
+      x[2] = __uint_as_float(v[8 * j + 2]) + b0.z; x[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
+      x[4] = __uint_as_float(v[8 * j + 4]) + b1.x; x[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
+      x[6] = __uint_as_float(v[8 * j + 6]) + b1.z; x[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
+      if (GELU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = quick_gelu(x[e]);
+      }
+      const uint32_t p0 = pack16x2(x[0], x[1], ep.fp16), p1 = pack16x2(x[2], x[3], ep.fp16);
+      const uint32_t p2 = pack16x2(x[4], x[5], ep.fp16), p3 = pack16x2(x[6], x[7], ep.fp16);
+      const uint32_t dst = buf + lane * 128 + ((j ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmC, buf, n0, row0);  // rows >= M / columns >= N are clipped by the tensor map
+      tma_store_commit();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// EPI_F32_RESID: fp32 out = acc + bias + resid, 32 columns (one 128-B fp32 box row) at a time.
+// ---------------------------------------------------------------------------------------------
+template <int STG_BUFS>
+__device__ __forceinline__ void resid_issue_load(const CUtensorMap* tmR, int N, int row0, int n0, EpiCtx& cx, int lane) {
+  if (n0 >= N) return;
+  if (lane == 0) {
+    tma_store_wait_read<0>();  // every earlier store has read its box (the target buffer is one of them)
+    const uint32_t bar = cx.rbar + 8u * (cx.n_load & 1u);
+    mbar_arrive_expect_tx(bar, BOX_BYTES);
+    tma_load_2d(cx.stg + (cx.n_load % STG_BUFS) * BOX_BYTES, tmR, bar, n0, row0);
+  }
+  ++cx.n_load;
+}
+
+template <int HALF_N, int STG_BUFS, bool PAIR>
+__device__ __forceinline__ void epilogue_f32_resid(const GemmEpilogue& ep, const CUtensorMap* tmC, const CUtensorMap* tmR,
+                                                   int N, int row0, int col0, uint32_t taddr, uint32_t tempty,
+                                                   EpiCtx& cx, int lane) {
+  constexpr int CHUNKS = HALF_N / 32;
+  // (the residual box of chunk 0 was requested by epilogue_tile before the accumulator was ready)
+#pragma unroll 1
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int n0 = col0 + 32 * c;
+    uint32_t v[32];
+    tmem_ld32(taddr + 32 * c, v);
+    // residual of the NEXT chunk: in flight while this one is processed (needs the second buffer)
+    if (STG_BUFS > 1 && c + 1 < CHUNKS) resid_issue_load<STG_BUFS>(tmR, N, row0, n0 + 32, cx, lane);
+    tmem_ld_wait();
+    if (c == CHUNKS - 1) release_accumulator<PAIR>(tempty, lane);
+    if (n0 >= N) continue;
+    const uint32_t buf = cx.stg + (cx.n_use % STG_BUFS) * BOX_BYTES;
+    mbar_wait(cx.rbar + 8u * (cx.n_use & 1u), (cx.n_use >> 1) & 1u);  // residual box has landed
+    ++cx.n_use;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // 4 columns -> one 16-B chunk
+      const int n = n0 + 4 * j;
+      const uint32_t a = buf + lane * 128 + ((j ^ (lane & 7)) << 4);
+      float4 r;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory");
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ep.bias && n + 4 <= N) b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+      r.x += __uint_as_float(v[4 * j + 0]) + b.x;
+      r.y += __uint_as_float(v[4 * j + 1]) + b.y;
+      r.z += __uint_as_float(v[4 * j + 2]) + b.z;
+      r.w += __uint_as_float(v[4 * j + 3]) + b.w;
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r.x), "f"(r.y), "f"(r.z), "f"(r.w) : "memory");
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmC, buf, n0, row0);
+      tma_store_commit();
+    }
+    if (STG_BUFS == 1 && c + 1 < CHUNKS) resid_issue_load<STG_BUFS>(tmR, N, row0, n0 + 32, cx, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// EPI_GENERIC: tcgen05.ld -> per-warp smem transpose -> alpha/bias/act/residual/row scatter -> coalesced stores.
+// ---------------------------------------------------------------------------------------------
+template <int HALF_N, bool PAIR>
+__device__ __forceinline__ void epilogue_generic(const GemmEpilogue& ep, int M, int N, int row0, int col0,
+                                                 uint32_t taddr, uint32_t tempty, uint32_t stg, int lane) {
+  constexpr int CHUNKS = HALF_N / 32;
+  // lane -> (sub-row lane/8, 16-B column chunk lane%8): one warp instruction touches 4 rows x 128 contiguous bytes
+  const int sub = lane >> 3, cj = lane & 7;
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
+#pragma unroll 1
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int n = col0 + 32 * c + 4 * cj;  // this lane's 4 output columns
     const bool col_ok = n + 4 <= N;
-    // residual prefetch (overlaps the TMEM load + staging)
     float4 rv[8];
     if (ep.resid) {
 #pragma unroll
@@ -98,24 +207,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
         }
       }
     }
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
     tmem_ld_wait();
     __syncwarp();  // previous chunk's read-back finished
-    // stage: TMEM lane (= tile row) `lane` -> 128-B smem row, 16-B chunks XOR-swizzled by row
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t dst = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[4 * j]),
-                   "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                   "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
                    : "memory");
     }
-    if (c + 1 < CHUNKS) {
-      tmem_ld_32x32b_x32(taddr + 32 * (c + 1), v);  // in flight during the emit phase
-    } else {
-      // accumulator fully drained: hand the TMEM stage back to the issuer
-      tc_fence_before();
-      if (PAIR) mbar_arrive_remote(tempty, 0);
-      else mbar_arrive(tempty);
-    }
+    if (c + 1 < CHUNKS) tmem_ld32(taddr + 32 * (c + 1), v);  // in flight during the emit phase
+    else release_accumulator<PAIR>(tempty, lane);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -123,13 +227,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
       const int m = row0 + r;
       float4 x;
       const uint32_t src = stg + r * 128 + ((cj ^ (r & 7)) << 4);
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                   : "r"(src)
-                   : "memory");
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(src) : "memory");
       if (m >= M || !col_ok) continue;
-      x.x = fmaf(ep.alpha, x.x, bv[c].x); x.y = fmaf(ep.alpha, x.y, bv[c].y);
-      x.z = fmaf(ep.alpha, x.z, bv[c].z); x.w = fmaf(ep.alpha, x.w, bv[c].w);
+      x.x = fmaf(ep.alpha, x.x, bv.x); x.y = fmaf(ep.alpha, x.y, bv.y);
+      x.z = fmaf(ep.alpha, x.z, bv.z); x.w = fmaf(ep.alpha, x.w, bv.w);
       if (ep.act == 1) {
         x.x = quick_gelu(x.x); x.y = quick_gelu(x.y);
         x.z = quick_gelu(x.z); x.w = quick_gelu(x.w);
@@ -137,22 +238,68 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
       if (ep.resid) { x.x += rv[i].x; x.y += rv[i].y; x.z += rv[i].z; x.w += rv[i].w; }
       long long orow = m;
       if (ep.row_grp > 0) orow = static_cast<long long>(m / ep.row_grp) * (ep.row_grp + 1) + 1 + m % ep.row_grp;
-      if (OUT_16) {
-        uint2 o;
-        o.x = pack16x2(x.x, x.y, ep.fp16);
-        o.y = pack16x2(x.z, x.w, ep.fp16);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + orow * ep.ldo + n) = o;
-      } else {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow * ep.ldo + n) = x;
-      }
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow * ep.ldo + n) = x;
     }
   }
 }
 
-template <int BLOCK_N, int OUT_BF16>
+// One 128 x BLOCK_N accumulator tile of this CTA (8 epilogue warps).  A warp may only read the TMEM lane quarter
+// (warp % 4); warps w and w+4 share a quarter and split the tile's columns in halves.
+// next_row0 < 0: no further tile for this CTA.
+template <int BLOCK_N, int MODE, int STG_BUFS, bool PAIR>
+__device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, const CUtensorMap* tmC, const CUtensorMap* tmR,
+                                              int M, int N, int tile_row0, int tile_col0, int next_row0, int next_col0,
+                                              uint32_t tmem_acc, uint32_t tfull, uint32_t tfull_phase, uint32_t tempty,
+                                              EpiCtx& cx, int warp, int lane) {
+  constexpr int HALF_N = BLOCK_N / 2;
+  const int ew = warp & 3, half = (warp - 4) >> 2;
+  const int row0 = tile_row0 + ew * 32;
+  const int col0 = tile_col0 + half * HALF_N;
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(ew * 32) << 16) + half * HALF_N;
+  if (MODE == EPI_F32_RESID) {
+    // first residual box of this tile: requested before the accumulator is even ready
+    if (row0 < M) resid_issue_load<STG_BUFS>(tmR, N, row0, col0, cx, lane);
+    // and the residual boxes of the NEXT tile are pulled into L2 a whole main loop ahead
+    if (next_row0 >= 0 && lane == 0) {
+      const int nr = next_row0 + ew * 32, nc = next_col0 + half * HALF_N;
+      if (nr < M)
+        for (int c = 0; c < HALF_N / 32; ++c)
+          if (nc + 32 * c < N) tma_prefetch_l2_2d(tmR, nc + 32 * c, nr);
+    }
+  }
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
+  if (row0 >= M) {  // warp entirely below the matrix: nothing to store, just release the accumulator
+    release_accumulator<PAIR>(tempty, lane);
+    return;
+  }
+  if (MODE == EPI_16) epilogue_16<HALF_N, false, STG_BUFS, PAIR>(ep, tmC, N, row0, col0, taddr, tempty, cx, lane);
+  else if (MODE == EPI_16_GELU) epilogue_16<HALF_N, true, STG_BUFS, PAIR>(ep, tmC, N, row0, col0, taddr, tempty, cx, lane);
+  else if (MODE == EPI_F32_RESID) epilogue_f32_resid<HALF_N, STG_BUFS, PAIR>(ep, tmC, tmR, N, row0, col0, taddr, tempty, cx, lane);
+  else epilogue_generic<HALF_N, PAIR>(ep, M, N, row0, col0, taddr, tempty, cx.stg, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1-CTA kernel
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 5;
+  static constexpr int STG_BUFS = (BLOCK_N == 256) ? 1 : 2;
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (256 or 512)
+  static constexpr uint32_t STG_BYTES = 8 * STG_BUFS * BOX_BYTES;
+  static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 8 * 16 + 16;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;  // + align slack
+};
+
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    int M, int N, int K, GemmEpilogue ep) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M, int N, int K,
+               GemmEpilogue ep) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -166,9 +313,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-  volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES + 8u * (2 * STAGES + 4));
+  const uint32_t rbar_base = bar_base + 8u * (2 * STAGES + 4);  // 8 warps x 2 residual-load barriers
+  const uint32_t tmem_slot = rbar_base + 8u * 16;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -181,6 +328,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (MODE != EPI_GENERIC) tma_prefetch_desc(&tmC);
+    if (MODE == EPI_F32_RESID) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -189,8 +338,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 256);
+      mbar_init(tempty_bar(s), 8);  // one arrive per epilogue warp
     }
+    for (int s = 0; s < 16; ++s) mbar_init(rbar_base + 8u * s, 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -247,13 +397,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
+    EpiCtx cx{stg_base + (warp - 4) * Cfg::STG_BUFS * BOX_BYTES, rbar_base + 16u * (warp - 4), 0u, 0u};
     uint32_t iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int nxt = tile + gridDim.x;
+      const int nrow = nxt < total_tiles ? (nxt / n_tiles) * BLOCK_M : -1, ncol = (nxt % n_tiles) * BLOCK_N;
       const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
-      epilogue_tile<BLOCK_N, OUT_BF16, false>(ep, M, N, m_blk * BLOCK_M, n_blk * BLOCK_N, tmem_base + as * BLOCK_N,
-                                              tfull_bar(as), aphase, tempty_bar(as), stg_base, warp, lane);
+      epilogue_tile<BLOCK_N, MODE, Cfg::STG_BUFS, false>(ep, &tmC, &tmR, M, N, m_blk * BLOCK_M, n_blk * BLOCK_N, nrow, ncol,
+                                                          tmem_base + as * BLOCK_N, tfull_bar(as), aphase,
+                                                          tempty_bar(as), cx, warp, lane);
     }
+    if (MODE != EPI_GENERIC && lane == 0) tma_store_wait<0>();  // all bulk stores complete before the CTA retires
   }
 
   tc_fence_before();
@@ -264,30 +419,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-
-// ---------------------------------------------------------------------------
-// CTA-pair variant (cta_group::2): two CTAs of a cluster on adjacent SMs compute one 256 x 256 tile.
-// Each CTA stages its own 128 A rows and HALF of the B tile (128 of the 256 weight rows) per k-block,
-// the leader's UMMA (M = 256) reads B from both CTAs' shared memory, and every CTA keeps its 128
-// accumulator rows in its own TMEM.  Per SM this halves the B traffic through shared memory
-// (TMA fill + UMMA read: 128 B/clk instead of 192 B/clk), which is what bounds the 1-CTA kernel.
-// ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2), 256 x 256 tiles
+// ---------------------------------------------------------------------------------------------
 struct PairCfg {
   static constexpr int BLOCK_N = 256;
   static constexpr int STAGES = 5;
+  static constexpr int STG_BUFS = 2;
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;          // 128 x 64
   static constexpr uint32_t B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;    // this CTA's half: 128 x 64
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 512;
-  static constexpr uint32_t STG_BYTES = 8 * 32 * 128;
-  static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
+  static constexpr uint32_t STG_BYTES = 8 * STG_BUFS * BOX_BYTES;
+  static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 8 * 16 + 16;
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
 };
 
-template <int OUT_16>
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    int M, int N, int K, GemmEpilogue ep) {
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M, int N,
+                    int K, GemmEpilogue ep) {
   using Cfg = PairCfg;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BLOCK_N = Cfg::BLOCK_N;
@@ -302,7 +454,8 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };           // per CTA (multicast commit)
   auto tfull_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + s); };       // per CTA (multicast commit)
   auto tempty_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + 2 + s); };  // used in the leader only
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t rbar_base = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t tmem_slot = rbar_base + 8u * 16;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5;
@@ -319,6 +472,8 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (MODE != EPI_GENERIC) tma_prefetch_desc(&tmC);
+    if (MODE == EPI_F32_RESID) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -327,8 +482,9 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 2 * 256);  // epilogue threads of both CTAs
+      mbar_init(tempty_bar(s), 16);  // one arrive per epilogue warp of both CTAs
     }
+    for (int s = 0; s < 16; ++s) mbar_init(rbar_base + 8u * s, 1);
     mbar_fence_init();
   }
   cluster_sync_all();  // barriers of both CTAs initialised before anyone signals across the pair
@@ -387,14 +543,19 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
+    EpiCtx cx{stg_base + (warp - 4) * Cfg::STG_BUFS * BOX_BYTES, rbar_base + 16u * (warp - 4), 0u, 0u};
     uint32_t iter = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++iter) {
       const int m_pair = tile / n_tiles, n_blk = tile % n_tiles;
+      const int nxt = tile + n_clusters;
+      const int nrow = nxt < total_tiles ? (nxt / n_tiles) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M : -1;
+      const int ncol = (nxt % n_tiles) * BLOCK_N;
       const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
-      epilogue_tile<BLOCK_N, OUT_16, true>(ep, M, N, m_pair * 2 * BLOCK_M + rank * BLOCK_M, n_blk * BLOCK_N,
-                                           tmem_base + as * BLOCK_N, tfull_bar(as), aphase, tempty_bar(as), stg_base,
-                                           warp, lane);
+      epilogue_tile<BLOCK_N, MODE, Cfg::STG_BUFS, true>(ep, &tmC, &tmR, M, N, m_pair * 2 * BLOCK_M + rank * BLOCK_M,
+                                                         n_blk * BLOCK_N, nrow, ncol, tmem_base + as * BLOCK_N,
+                                                         tfull_bar(as), aphase, tempty_bar(as), cx, warp, lane);
     }
+    if (MODE != EPI_GENERIC && lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -408,42 +569,61 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
-template <int BLOCK_N, int OUT_BF16>
+struct Maps {
+  CUtensorMap a, b, c, r;
+};
+
+int build_maps(Maps& mp, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+               const GemmEpilogue& ep, int mode, int b_box_rows) {
+  int rc = make_tmap_16b(&mp.a, A, M, K, lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap_16b(&mp.b, B, N, K, ldb, b_box_rows);
+  if (rc) return rc;
+  mp.c = mp.a;
+  mp.r = mp.a;  // placeholders for modes that do not use them
+  if (mode == EPI_16 || mode == EPI_16_GELU) {
+    rc = make_tmap_2d(&mp.c, ep.out, 2, M, N, ep.ldo, 32, 64);
+    if (rc) return rc;
+  } else if (mode == EPI_F32_RESID) {
+    rc = make_tmap_2d(&mp.c, ep.out, 4, M, N, ep.ldo, 32, 32);
+    if (rc) return rc;
+    rc = make_tmap_2d(&mp.r, ep.resid, 4, M, N, ep.ldr, 32, 32);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+template <int BLOCK_N, int MODE>
 int launch(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
            const GemmEpilogue& ep, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  CUtensorMap tmA, tmB;
-  int rc = make_tmap_16b(&tmA, A, M, K, lda, BLOCK_M);
+  Maps mp;
+  int rc = build_maps(mp, A, lda, B, ldb, M, N, K, ep, MODE, BLOCK_N);
   if (rc) return rc;
-  rc = make_tmap_16b(&tmB, B, N, K, ldb, BLOCK_N);
-  if (rc) return rc;
-  auto kern = gemm_tn_kernel<BLOCK_N, OUT_BF16>;
+  auto kern = gemm_tn_kernel<BLOCK_N, MODE>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    OVMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::SMEM_BYTES));
+    OVMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, stream);  // work = algorithmic FLOPs
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mp.a, mp.b, mp.c, mp.r, M, N, K, ep);
   OVMR_CHECK_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
 }
 
-template <int OUT_16>
+template <int MODE>
 int launch_pair(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                 const GemmEpilogue& ep, cudaStream_t stream) {
   using Cfg = PairCfg;
-  CUtensorMap tmA, tmB;
-  int rc = make_tmap_16b(&tmA, A, M, K, lda, BLOCK_M);
+  Maps mp;
+  int rc = build_maps(mp, A, lda, B, ldb, M, N, K, ep, MODE, Cfg::BLOCK_N / 2);
   if (rc) return rc;
-  rc = make_tmap_16b(&tmB, B, N, K, ldb, Cfg::BLOCK_N / 2);
-  if (rc) return rc;
-  auto kern = gemm_tn_pair_kernel<OUT_16>;
+  auto kern = gemm_tn_pair_kernel<MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -454,16 +634,24 @@ int launch_pair(const void* A, long long lda, const void* B, long long ldb, int 
   const int max_clusters = num_sms() / 2;
   const int clusters = total < max_clusters ? total : max_clusters;
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, stream);
-  kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+  kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mp.a, mp.b, mp.c, mp.r, M, N, K, ep);
   OVMR_CHECK_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
 }
 
+template <int MODE>
+int dispatch_tile(int bn, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                  const GemmEpilogue& ep, cudaStream_t stream) {
+  if (bn == 512) return launch_pair<MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+  if (bn == 256) return launch<256, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+  return launch<128, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+}
+
 }  // namespace
 
 int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
-                 const GemmEpilogue& ep, cudaStream_t stream, int force_block_n) {
+            const GemmEpilogue& ep, cudaStream_t stream, int force_block_n) {
   OVMR_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   OVMR_REQUIRE(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0,
                "gemm: K, N, lda, ldb must be multiples of 8 (K=%d N=%d lda=%lld ldb=%lld)", K, N, lda, ldb);
@@ -471,29 +659,34 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, i
                    (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0,
                "gemm: operands must be 16-byte aligned");
   OVMR_REQUIRE(ep.out != nullptr && ep.ldo >= N, "gemm: bad output (ldo=%lld, N=%d)", ep.ldo, N);
+  OVMR_REQUIRE(!ep.out_bf16 || (ep.resid == nullptr && ep.row_grp == 0 && ep.alpha == 1.0f),
+               "gemm: 16-bit output supports bias and QuickGELU only");
+  // ---- tile shape
   int bn = force_block_n;
-  if (bn == 0 || bn == 512) {
-    // CTA-pair kernel (256 x 256 tiles over two SMs) whenever there are enough tiles to fill the pairs
-    const long long pair_tiles = static_cast<long long>((M + 255) / 256) * ((N + 255) / 256);
-    if (bn == 512 || (N >= 256 && pair_tiles >= num_sms() / 2))
-      return ep.out_bf16 ? launch_pair<1>(A, lda, B, ldb, M, N, K, ep, stream)
-                         : launch_pair<0>(A, lda, B, ldb, M, N, K, ep, stream);
-  }
   if (bn == 0) {
-    // wave-quantisation heuristic: cost ~ waves x tile width
     const int sms = num_sms();
-    const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-    const long long w256 = (m_tiles * ((N + 255) / 256) + sms - 1) / sms * 256;
-    const long long w128 = (m_tiles * ((N + 127) / 128) + sms - 1) / sms * 128;
-    bn = (w256 <= w128 + w128 / 16) ? 256 : 128;
+    const long long pair_tiles = static_cast<long long>((M + 255) / 256) * ((N + 255) / 256);
+    if (N >= 256 && pair_tiles >= sms / 2) {
+      bn = 512;  // CTA-pair kernel whenever there are enough 256 x 256 tiles to fill the pairs
+    } else {
+      // wave-quantisation heuristic for the 1-CTA kernels: cost ~ waves x tile width
+      const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+      const long long w256 = (m_tiles * ((N + 255) / 256) + sms - 1) / sms * 256;
+      const long long w128 = (m_tiles * ((N + 127) / 128) + sms - 1) / sms * 128;
+      bn = (w256 <= w128 + w128 / 16) ? 256 : 128;
+    }
   }
-  OVMR_REQUIRE(bn == 128 || bn == 256, "gemm: block_n must be 128 or 256 (got %d)", bn);
-  if (bn == 256) {
-    return ep.out_bf16 ? launch<256, 1>(A, lda, B, ldb, M, N, K, ep, stream)
-                       : launch<256, 0>(A, lda, B, ldb, M, N, K, ep, stream);
+  OVMR_REQUIRE(bn == 128 || bn == 256 || bn == 512, "gemm: block_n must be 128, 256 or 512 (pair) (got %d)", bn);
+  // ---- epilogue mode
+  if (ep.out_bf16) {
+    OVMR_REQUIRE(ep.ldo % 8 == 0, "gemm: 16-bit output needs ldo %% 8 == 0");
+    return ep.act == 1 ? dispatch_tile<EPI_16_GELU>(bn, A, lda, B, ldb, M, N, K, ep, stream)
+                       : dispatch_tile<EPI_16>(bn, A, lda, B, ldb, M, N, K, ep, stream);
   }
-  return ep.out_bf16 ? launch<128, 1>(A, lda, B, ldb, M, N, K, ep, stream)
-                     : launch<128, 0>(A, lda, B, ldb, M, N, K, ep, stream);
+  const bool tma_resid = ep.resid != nullptr && ep.row_grp == 0 && ep.act == 0 && ep.alpha == 1.0f && ep.ldo % 4 == 0 &&
+                         ep.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0;
+  if (tma_resid) return dispatch_tile<EPI_F32_RESID>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+  return dispatch_tile<EPI_GENERIC>(bn, A, lda, B, ldb, M, N, K, ep, stream);
 }
 
 }  // namespace ovmr

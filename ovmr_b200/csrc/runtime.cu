@@ -101,29 +101,38 @@ PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 
 }  // namespace
 
-// 16-bit row-major [rows, cols] (cols contiguous, leading dim ld) -> tiles of box_rows x 64, 128B swizzle
-int make_tmap_16b(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
-                   int box_rows) {
+// Row-major [rows, cols] matrix (cols contiguous, leading dim ld elements) -> TMA boxes of box_rows x box_cols
+// elements whose inner extent is exactly 128 bytes, 128-byte swizzle, zero fill / clipping out of bounds.
+int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, long long rows, long long cols, long long ld,
+                 int box_rows, int box_cols) {
   auto enc = tensor_map_encoder();
   if (!enc) {
     set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
     return OVMR_ERR_INVALID;
   }
+  if (box_cols * elem_bytes != 128 || (elem_bytes != 2 && elem_bytes != 4)) {
+    set_last_error("make_tmap_2d: box inner extent must be 128 bytes (box_cols=%d elem_bytes=%d)", box_cols, elem_bytes);
+    return OVMR_ERR_INVALID;
+  }
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  // 16-bit payloads are moved as opaque 16-bit words (bf16 and fp16 alike)
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled failed (%d) base=%p rows=%lld cols=%lld ld=%lld box_rows=%d",
-                   (int)r, base, rows, cols, ld, box_rows);
+    set_last_error("cuTensorMapEncodeTiled failed (%d) base=%p rows=%lld cols=%lld ld=%lld box=%dx%d elem=%d", (int)r, base,
+                   rows, cols, ld, box_rows, box_cols, elem_bytes);
     return OVMR_ERR_INVALID;
   }
   return 0;
 }
 
+int make_tmap_16b(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  return make_tmap_2d(map, base, 2, rows, cols, ld, box_rows, 64);
+}
 
 int num_sms() {
   static int cached[64] = {0};
