@@ -114,54 +114,52 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t idesc_s = umma_idesc_16b_f32(QTILE, Lpad, FP16 ? 1 : 0);
       const uint32_t idesc_o = umma_idesc_16b_f32_bmn(QTILE, 64, FP16 ? 1 : 0);
       const int ksteps = Lpad / 16;
-      // PV of the previous tile is issued AFTER S of the current one (software pipeline)
-      bool have_prev = false;
-      uint32_t prev_t = 0, prev_ks = 0;
-      bool prev_last = false;
-      auto issue_pv = [&](uint32_t t, uint32_t ks, bool last_of_work) {
-        const uint32_t r = t & 1u, n = t >> 1;
-        mbar_wait(p_full(r), n & 1u);
-        tc_fence_after();
-        const uint32_t region = tmem_base + r * 256u;
-        const uint64_t v_desc = umma_desc_mn_sw128(sV + ks * kv_stride, kv_bytes);
-        for (int kk = 0; kk < ksteps; ++kk) {
-          // 16 keys per step: 8 packed TMEM columns of P, 16 rows (2048 B) of V
-          umma_16b_ts(region + 128u, region + 8u * kk, v_desc + 128u * kk, idesc_o, kk != 0 ? 1u : 0u);
-        }
-        umma_commit(o_full(r));
-        if (last_of_work) umma_commit(kv_empty(ks));
-      };
-      uint32_t t = 0, wi = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
-        const uint32_t ks = wi & 1u, kn = wi >> 1;
-        for (int j = 0; j < nqt; ++j, ++t) {
-          const uint32_t r = t & 1u, n = t >> 1, qs = t & 1u;
-          mbar_wait(r_free(r), (n & 1u) ^ 1u);   // softmax group has drained O of the tile 2 steps back
-          mbar_wait(q_full(qs), n & 1u);
-          if (j == 0) mbar_wait(kv_full(ks), kn & 1u);
-          tc_fence_after();
-          const uint64_t q_desc = umma_desc_k_sw128(sQ + qs * Q_BYTES);
-          const uint64_t k_desc = umma_desc_k_sw128(sK + ks * kv_stride);
+      // Event-driven issue order: S of the next tile goes out as soon as its TMEM region, Q and K/V are ready;
+      // P V of the oldest pending tile goes out as soon as its softmax group has written P.  Neither waits
+      // behind the other (the two softmax groups would otherwise serialise on this thread).
+      const int my_works = (n_work - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+      const uint32_t T = static_cast<uint32_t>(my_works) * nqt;   // tiles of this CTA
+      uint32_t next_s = 0, next_pv = 0;
+      while (next_pv < T) {
+        if (next_s < T && next_s < next_pv + 2) {
+          const uint32_t t = next_s, wi = t / nqt, j = t % nqt;
+          const uint32_t r = t & 1u, n = t >> 1, qs = t & 1u, ks = wi & 1u, kn = wi >> 1;
+          if (mbar_try_wait(r_free(r), (n & 1u) ^ 1u) && mbar_try_wait(q_full(qs), n & 1u) &&
+              (j != 0 || mbar_try_wait(kv_full(ks), kn & 1u))) {
+            tc_fence_after();
+            const uint64_t q_desc = umma_desc_k_sw128(sQ + qs * Q_BYTES);
+            const uint64_t k_desc = umma_desc_k_sw128(sK + ks * kv_stride);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_base + r * 256u, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(s_full(r));
-          umma_commit(q_empty(qs));
-          if (have_prev) issue_pv(prev_t, prev_ks, prev_last);
-          have_prev = true;
-          prev_t = t;
-          prev_ks = ks;
-          prev_last = (j == nqt - 1);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tmem_base + r * 256u, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+            umma_commit(s_full(r));
+            umma_commit(q_empty(qs));
+            ++next_s;
+          }
+        }
+        if (next_pv < next_s) {
+          const uint32_t t = next_pv, wi = t / nqt, j = t % nqt;
+          const uint32_t r = t & 1u, n = t >> 1, ks = wi & 1u;
+          if (mbar_try_wait(p_full(r), n & 1u)) {
+            tc_fence_after();
+            const uint32_t region = tmem_base + r * 256u;
+            const uint64_t v_desc = umma_desc_mn_sw128(sV + ks * kv_stride, kv_bytes);
+            for (int kk = 0; kk < ksteps; ++kk) {
+              // 16 keys per step: 8 packed TMEM columns of P, 16 rows (2048 B) of V
+              umma_16b_ts(region + 128u, region + 8u * kk, v_desc + 128u * kk, idesc_o, kk != 0 ? 1u : 0u);
+            }
+            umma_commit(o_full(r));
+            if (j == static_cast<uint32_t>(nqt) - 1) umma_commit(kv_empty(ks));
+            ++next_pv;
+          }
         }
       }
-      if (have_prev) issue_pv(prev_t, prev_ks, prev_last);
     }
   } else if (warp >= 4) {
     // ===================== softmax + output (two groups of 4 warps) =====================
     const uint32_t grp = (warp - 4) >> 2;       // handles tiles with (t & 1) == grp
     const uint32_t quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;        // query row inside the tile
-    const int nchunk = Lpad / 16;
     uint32_t t = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int seq = w / heads, h = w % heads;
@@ -173,32 +171,103 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(s_full(r), n & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (quarter * 32u << 16) + r * 256u;
+        // The S row is read twice from TMEM (max, then exp) in 32-column chunks with the next chunk's
+        // tcgen05.ld in flight while the current one is processed; masking predicates are evaluated only in
+        // chunks that straddle the last visible key.
+        const int n32 = Lpad >> 5;
+        const bool tail16 = (Lpad & 31) != 0;
         // ---- pass 1: masked row max
         float m = -INFINITY;
-        for (int c = 0; c < nchunk; ++c) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(taddr + 16 * c, v);
-          tmem_ld_wait();
+        {
+          uint32_t va[32], vb[32];
+          auto maxchunk = [&](const uint32_t* v, int base, int cnt) {
+            if (base + cnt - 1 <= kmax) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (16 * c + e <= kmax) m = fmaxf(m, __uint_as_float(v[e]));
+              for (int e = 0; e < 32; ++e)
+                if (e < cnt) m = fmaxf(m, __uint_as_float(v[e]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (e < cnt && base + e <= kmax) m = fmaxf(m, __uint_as_float(v[e]));
+            }
+          };
+          if (n32 > 0) tmem_ld32(taddr, va);
+          int c = 0;
+#pragma unroll 1
+          while (c < n32) {
+            tmem_ld_wait();
+            if (c + 1 < n32) tmem_ld32(taddr + 32 * (c + 1), vb);
+            maxchunk(va, 32 * c, 32);
+            if (++c >= n32) break;
+            tmem_ld_wait();
+            if (c + 1 < n32) tmem_ld32(taddr + 32 * (c + 1), va);
+            maxchunk(vb, 32 * c, 32);
+            ++c;
+          }
+          if (tail16) {
+            uint32_t vt[16];
+            tmem_ld_32x32b_x16(taddr + 32 * n32, vt);
+            tmem_ld_wait();
+            maxchunk(vt, 32 * n32, 16);
+          }
         }
         const float ms = (m == -INFINITY) ? 0.f : m * scale_log2e;
         // ---- pass 2: exp2, row sum, pack, write P over S
         float sum = 0.f;
-        for (int c = 0; c < nchunk; ++c) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(taddr + 16 * c, v);
-          tmem_ld_wait();
-          uint32_t pk[8];
+        {
+          uint32_t va[32], vb[32];
+          auto expchunk = [&](const uint32_t* v, int base, int cnt) {
+            uint32_t pk[16];
+            if (base + cnt - 1 <= kmax) {
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            const float p0 = (16 * c + e <= kmax) ? ex2f(fmaf(__uint_as_float(v[e]), scale_log2e, -ms)) : 0.f;
-            const float p1 = (16 * c + e + 1 <= kmax) ? ex2f(fmaf(__uint_as_float(v[e + 1]), scale_log2e, -ms)) : 0.f;
-            sum += p0 + p1;
-            pk[e >> 1] = FP16 ? pack_f16x2(p0, p1) : pack_bf16x2(p0, p1);
+              for (int e = 0; e < 32; e += 2) {
+                if (e < cnt) {
+                  const float p0 = ex2f(fmaf(__uint_as_float(v[e]), scale_log2e, -ms));
+                  const float p1 = ex2f(fmaf(__uint_as_float(v[e + 1]), scale_log2e, -ms));
+                  sum += p0 + p1;
+                  pk[e >> 1] = FP16 ? pack_f16x2(p0, p1) : pack_bf16x2(p0, p1);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; e += 2) {
+                if (e < cnt) {
+                  const float p0 = (base + e <= kmax) ? ex2f(fmaf(__uint_as_float(v[e]), scale_log2e, -ms)) : 0.f;
+                  const float p1 = (base + e + 1 <= kmax) ? ex2f(fmaf(__uint_as_float(v[e + 1]), scale_log2e, -ms)) : 0.f;
+                  sum += p0 + p1;
+                  pk[e >> 1] = FP16 ? pack_f16x2(p0, p1) : pack_bf16x2(p0, p1);
+                }
+              }
+            }
+            if (cnt == 32) {
+              tmem_st_32x32b_x16(taddr + (base >> 1), pk);
+            } else {
+              const uint32_t (&pk8)[8] = *reinterpret_cast<const uint32_t (*)[8]>(&pk[0]);
+              tmem_st_32x32b_x8(taddr + (base >> 1), pk8);
+            }
+          };
+          if (n32 > 0) tmem_ld32(taddr, va);
+          int c = 0;
+#pragma unroll 1
+          while (c < n32) {
+            tmem_ld_wait();
+            if (c + 1 < n32) tmem_ld32(taddr + 32 * (c + 1), vb);
+            expchunk(va, 32 * c, 32);
+            if (++c >= n32) break;
+            tmem_ld_wait();
+            if (c + 1 < n32) tmem_ld32(taddr + 32 * (c + 1), va);
+            expchunk(vb, 32 * c, 32);
+            ++c;
           }
-          tmem_st_32x32b_x8(taddr + 8 * c, pk);
+          if (tail16) {
+            uint32_t vt[32];
+            const uint32_t (&dummy)[16] = *reinterpret_cast<const uint32_t (*)[16]>(&vt[0]);
+            (void)dummy;
+            uint32_t (&vt16)[16] = *reinterpret_cast<uint32_t (*)[16]>(&vt[0]);
+            tmem_ld_32x32b_x16(taddr + 32 * n32, vt16);
+            tmem_ld_wait();
+            expchunk(vt, 32 * n32, 16);
+          }
         }
         tmem_st_wait();
         tc_fence_before();
