@@ -2,6 +2,8 @@
 // sm_100a kernels together: Transformer.forward, VisionTransformer.forward, the text read-out.
 #include "../../include/ovmr_b200.h"
 
+#include <cstdlib>
+
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
@@ -39,6 +41,27 @@ TransformerWs carve_transformer_ws(void* base, long long rows, int width) {
   return w;
 }
 
+// Alternating sweep direction.  Every kernel of a tower streams over the same token rows; an activation of a
+// 256-image batch (77-310 MB) does not fit the 126 MB L2, so a consumer that starts where its producer STARTED
+// finds nothing resident.  Each kernel therefore walks the rows in the opposite direction to the one before it:
+// the rows the producer wrote last (still in L2) are consumed first.  OVMR_SWEEP=0 disables (A/B measurements).
+struct Sweep {
+  int dir = 0;
+  bool on = true;
+  Sweep() {
+    static const bool enabled = [] {
+      const char* e = getenv("OVMR_SWEEP");
+      return e == nullptr || e[0] != '0';
+    }();
+    on = enabled;
+  }
+  int next() {
+    const int d = dir;
+    if (on) dir ^= 1;
+    return d;
+  }
+};
+
 #define RET_IF(expr)        \
   do {                      \
     int _rc = (expr);       \
@@ -56,31 +79,33 @@ int check_transformer(const ovmr_transformer* t) {
 
 // One pre-LN residual block on the fp32 residual stream x [rows, D] (clip/model.py:191-194).
 int run_block(const ovmr_block_weights& bw, float* x, int n_seq, int seq_len, int D, int heads, int causal,
-              int fp16, const TransformerWs& ws, bool ln1_done, cudaStream_t st) {
+              int fp16, const TransformerWs& ws, bool ln1_done, Sweep& sw, cudaStream_t st) {
   const int rows = n_seq * seq_len;
   // x + attn(ln_1(x))
   if (!ln1_done)
-    RET_IF(ovmr::layernorm(x, D, rows, D, nullptr, 0, bw.ln1_w, bw.ln1_b, nullptr, 0, ws.a_bf16, D, nullptr, nullptr, fp16, st));
+    RET_IF(ovmr::layernorm(x, D, rows, D, nullptr, 0, bw.ln1_w, bw.ln1_b, nullptr, 0, ws.a_bf16, D, nullptr, nullptr, fp16, st,
+                           sw.next()));
   GemmEpilogue qkv;
-  qkv.bias = bw.qkv_b; qkv.out = ws.big_bf16; qkv.ldo = 3LL * D; qkv.out_bf16 = 1; qkv.fp16 = fp16;
+  qkv.bias = bw.qkv_b; qkv.out = ws.big_bf16; qkv.ldo = 3LL * D; qkv.out_bf16 = 1; qkv.fp16 = fp16; qkv.reverse = sw.next();
   RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.qkv_w, D, rows, 3 * D, D, qkv, st));
-  RET_IF(ovmr::attention(ws.big_bf16, ws.a_bf16, n_seq, seq_len, D, heads, causal, fp16, st));
+  RET_IF(ovmr::attention(ws.big_bf16, ws.a_bf16, n_seq, seq_len, D, heads, causal, fp16, st, sw.next()));
   GemmEpilogue op;
-  op.bias = bw.out_b; op.resid = x; op.ldr = D; op.out = x; op.ldo = D; op.out_bf16 = 0; op.fp16 = fp16;
+  op.bias = bw.out_b; op.resid = x; op.ldr = D; op.out = x; op.ldo = D; op.out_bf16 = 0; op.fp16 = fp16; op.reverse = sw.next();
   RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.out_w, D, rows, D, D, op, st));
   // x + c_proj(QuickGELU(c_fc(ln_2(x))))
-  RET_IF(ovmr::layernorm(x, D, rows, D, nullptr, 0, bw.ln2_w, bw.ln2_b, nullptr, 0, ws.a_bf16, D, nullptr, nullptr, fp16, st));
+  RET_IF(ovmr::layernorm(x, D, rows, D, nullptr, 0, bw.ln2_w, bw.ln2_b, nullptr, 0, ws.a_bf16, D, nullptr, nullptr, fp16, st,
+                         sw.next()));
   GemmEpilogue fc;
-  fc.bias = bw.fc_b; fc.out = ws.big_bf16; fc.ldo = 4LL * D; fc.out_bf16 = 1; fc.act = 1; fc.fp16 = fp16;
+  fc.bias = bw.fc_b; fc.out = ws.big_bf16; fc.ldo = 4LL * D; fc.out_bf16 = 1; fc.act = 1; fc.fp16 = fp16; fc.reverse = sw.next();
   RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.fc_w, D, rows, 4 * D, D, fc, st));
   GemmEpilogue pj;
-  pj.bias = bw.proj_b; pj.resid = x; pj.ldr = D; pj.out = x; pj.ldo = D; pj.out_bf16 = 0; pj.fp16 = fp16;
+  pj.bias = bw.proj_b; pj.resid = x; pj.ldr = D; pj.out = x; pj.ldo = D; pj.out_bf16 = 0; pj.fp16 = fp16; pj.reverse = sw.next();
   RET_IF(ovmr::gemm_tn(ws.big_bf16, 4LL * D, bw.proj_w, 4LL * D, rows, D, 4 * D, pj, st));
   return 0;
 }
 
 int run_transformer(const ovmr_transformer* t, float* x, int n_seq, int seq_len, int causal, void* wsp,
-                    size_t ws_bytes, bool first_ln1_done, cudaStream_t st) {
+                    size_t ws_bytes, bool first_ln1_done, Sweep& sw, cudaStream_t st) {
   RET_IF(check_transformer(t));
   OVMR_REQUIRE(n_seq > 0 && seq_len > 0, "transformer: empty input (n_seq=%d seq_len=%d)", n_seq, seq_len);
   const long long rows = static_cast<long long>(n_seq) * seq_len;
@@ -90,7 +115,7 @@ int run_transformer(const ovmr_transformer* t, float* x, int n_seq, int seq_len,
   const TransformerWs ws = carve_transformer_ws(wsp, rows, t->width);
   for (int l = 0; l < t->layers; ++l) {
     RET_IF(run_block(t->blocks[l], x, n_seq, seq_len, t->width, t->heads, causal, t->fp16 != 0, ws,
-                     l == 0 && first_ln1_done, st));
+                     l == 0 && first_ln1_done, sw, st));
   }
   return 0;
 }
@@ -134,7 +159,8 @@ size_t ovmr_text_workspace_bytes(const ovmr_text* t, int n_seq, int seq_len) {
 int ovmr_transformer_forward(const ovmr_transformer* t, float* x, int n_seq, int seq_len, int causal, void* workspace,
                              size_t workspace_bytes, void* stream) {
   OVMR_REQUIRE(x != nullptr, "transformer_forward: null x");
-  return run_transformer(t, x, n_seq, seq_len, causal, workspace, workspace_bytes, false, S(stream));
+  Sweep sw;
+  return run_transformer(t, x, n_seq, seq_len, causal, workspace, workspace_bytes, false, sw, S(stream));
 }
 
 int ovmr_vit_forward(const ovmr_vit* v, const float* images, int batch, float* features, int normalize,
@@ -169,12 +195,15 @@ int ovmr_vit_forward(const ovmr_vit* v, const float* images, int batch, float* f
   RET_IF(ovmr::cls_rows(x, v->class_embedding, v->positional_embedding, batch, L, D, st));
   GemmEpilogue pe;
   pe.resid = v->positional_embedding; pe.ldr = D; pe.out = x; pe.ldo = D; pe.out_bf16 = 0; pe.row_grp = G * G; pe.fp16 = fp16;
+  Sweep sw;
+  sw.next();  // patchify walked the images first-to-last
+  pe.reverse = sw.next();
   RET_IF(ovmr::gemm_tn(patches, v->k_pad, v->conv_w, v->k_pad, batch * G * G, D, v->k_pad, pe, st));
   // ln_pre (fp32, in place) chained with layer 0's ln_1 (bf16 operand of the first QKV GEMM)
   const ovmr_block_weights& b0 = v->transformer.blocks[0];
   RET_IF(ovmr::layernorm(x, D, static_cast<int>(rows), D, nullptr, 0, v->ln_pre_w, v->ln_pre_b, x, D, ws.a_bf16, D,
-                         b0.ln1_w, b0.ln1_b, fp16, st));
-  RET_IF(run_transformer(&v->transformer, x, batch, L, 0, tws, tws_bytes, true, st));
+                         b0.ln1_w, b0.ln1_b, fp16, st, sw.next()));
+  RET_IF(run_transformer(&v->transformer, x, batch, L, 0, tws, tws_bytes, true, sw, st));
   // ln_post on the CLS rows, projection, optional L2 normalisation
   RET_IF(ovmr::layernorm(x, D, batch, D, nullptr, L, v->ln_post_w, v->ln_post_b, nullptr, 0, cls_bf16, D, nullptr,
                          nullptr, fp16, st));
@@ -198,7 +227,8 @@ int ovmr_text_forward(const ovmr_text* t, float* x, const int* eos_index, int n_
   const long long rows = static_cast<long long>(n_seq) * seq_len;
   const size_t tws_bytes = ovmr_transformer_workspace_bytes(rows, W);
   void* eot_bf16 = reinterpret_cast<uint8_t*>(workspace) + tws_bytes;
-  RET_IF(run_transformer(&t->transformer, x, n_seq, seq_len, 1, workspace, tws_bytes, false, st));
+  Sweep sw;
+  RET_IF(run_transformer(&t->transformer, x, n_seq, seq_len, 1, workspace, tws_bytes, false, sw, st));
   const int fp16 = t->transformer.fp16 != 0;
   RET_IF(ovmr::layernorm(x, W, n_seq, W, eos_index, seq_len, t->ln_final_w, t->ln_final_b, nullptr, 0, eot_bf16, W,
                          nullptr, nullptr, fp16, st));

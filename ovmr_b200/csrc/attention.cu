@@ -72,6 +72,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 
   const int qt = blockIdx.x, h = blockIdx.y, seq = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_wait();
   const int g = lane >> 2, t = lane & 3;
   const long long ld = 3LL * D;
   const __nv_bfloat16* base = qkv + static_cast<long long>(seq) * L * ld + h * HD;
@@ -215,7 +216,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 
 }  // namespace
 
-int attention(const void* qkv, void* out, int n_seq, int L, int D, int heads, int causal, int fp16, cudaStream_t stream) {
+int attention(const void* qkv, void* out, int n_seq, int L, int D, int heads, int causal, int fp16, cudaStream_t stream,
+              int reverse) {
   OVMR_REQUIRE(n_seq > 0 && L > 0 && heads > 0 && D == heads * HD, "attention: need D == heads*64 (D=%d heads=%d L=%d)", D,
                heads, L);
   // shape specialisation: the vision towers' sequence lengths run on the tcgen05 kernel; short sequences (text,
@@ -224,7 +226,7 @@ int attention(const void* qkv, void* out, int n_seq, int L, int D, int heads, in
     const char* e = getenv("OVMR_ATTN_IMPL");
     return e == nullptr ? 0 : (!strcmp(e, "legacy") ? 1 : (!strcmp(e, "tc") ? 2 : 0));
   }();
-  if (L <= 256 && (impl == 2 || (impl == 0 && L > 64))) return attention_tc(qkv, out, n_seq, L, D, heads, causal, fp16, stream);
+  if (L <= 256 && (impl == 2 || (impl == 0 && L > 64))) return attention_tc(qkv, out, n_seq, L, D, heads, causal, fp16, stream, reverse);
   OVMR_REQUIRE(n_seq <= 65535 && heads <= 65535, "attention: grid limits (n_seq=%d)", n_seq);
   const int nkb = (L + KB - 1) / KB;
   const size_t smem = (static_cast<size_t>(2) * nkb * KB + QT) * PITCH * 2;
@@ -239,12 +241,11 @@ int attention(const void* qkv, void* out, int n_seq, int L, int D, int heads, in
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   ProfScope prof(PROF_ATTENTION, 4.0 * n_seq * heads * static_cast<double>(L) * L * HD * (causal ? 0.5 : 1.0), stream);
   if (fp16)
-    attention_kernel<true><<<grid, 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                         reinterpret_cast<__nv_bfloat16*>(out), L, D, causal, scale_log2e);
+    OVMR_CHECK_CUDA(launch_pdl(attention_kernel<true>, grid, dim3(128), smem, stream, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                               reinterpret_cast<__nv_bfloat16*>(out), L, D, causal, scale_log2e));
   else
-    attention_kernel<false><<<grid, 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                          reinterpret_cast<__nv_bfloat16*>(out), L, D, causal, scale_log2e);
-  OVMR_CHECK_CUDA(cudaGetLastError());
+    OVMR_CHECK_CUDA(launch_pdl(attention_kernel<false>, grid, dim3(128), smem, stream, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                               reinterpret_cast<__nv_bfloat16*>(out), L, D, causal, scale_log2e));
   count_launches(1);
   return 0;
 }

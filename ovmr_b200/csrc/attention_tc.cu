@@ -36,7 +36,7 @@ template <bool FP16>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                     void* __restrict__ out_, int n_seq, int L, int Lpad, int D, int heads, int causal,
-                    float scale_log2e) {
+                    float scale_log2e, int reverse) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -88,13 +88,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       uint32_t t = 0, wi = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
-        const int seq = w / heads, h = w % heads;
+        const int we = reverse ? n_work - 1 - w : w;
+        const int seq = we / heads, h = we % heads;
         const uint32_t ks = wi & 1u, kn = wi >> 1;
         mbar_wait(kv_empty(ks), (kn & 1u) ^ 1u);
         mbar_arrive_expect_tx(kv_full(ks), 2 * kv_bytes);
@@ -162,7 +164,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int row = quarter * 32 + lane;        // query row inside the tile
     uint32_t t = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int seq = w / heads, h = w % heads;
+      const int we = reverse ? n_work - 1 - w : w;
+      const int seq = we / heads, h = we % heads;
       for (int j = 0; j < nqt; ++j, ++t) {
         if ((t & 1u) != grp) continue;
         const uint32_t r = grp, n = t >> 1;
@@ -313,7 +316,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }  // namespace
 
 int attention_tc(const void* qkv, void* out, int n_seq, int L, int D, int heads, int causal, int fp16,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, int reverse) {
   OVMR_REQUIRE(L > 0 && L <= 256 && D == heads * 64, "attention_tc: need L <= 256 and D == heads*64 (L=%d D=%d)", L, D);
   const int Lpad = (L + 15) / 16 * 16;
   const long long rows = static_cast<long long>(n_seq) * L;
@@ -336,10 +339,11 @@ int attention_tc(const void* qkv, void* out, int n_seq, int L, int D, int heads,
   const float scale_log2e = 0.125f * 1.4426950408889634f;
   ProfScope prof(PROF_ATTENTION, 4.0 * n_seq * heads * static_cast<double>(L) * L * 64 * (causal ? 0.5 : 1.0), stream);
   if (fp16)
-    attention_tc_kernel<true><<<grid, ATC_THREADS, smem, stream>>>(tmQ, tmKV, out, n_seq, L, Lpad, D, heads, causal, scale_log2e);
+    OVMR_CHECK_CUDA(launch_pdl(attention_tc_kernel<true>, dim3(grid), dim3(ATC_THREADS), smem, stream, tmQ, tmKV, out, n_seq, L,
+                               Lpad, D, heads, causal, scale_log2e, reverse));
   else
-    attention_tc_kernel<false><<<grid, ATC_THREADS, smem, stream>>>(tmQ, tmKV, out, n_seq, L, Lpad, D, heads, causal, scale_log2e);
-  OVMR_CHECK_CUDA(cudaGetLastError());
+    OVMR_CHECK_CUDA(launch_pdl(attention_tc_kernel<false>, dim3(grid), dim3(ATC_THREADS), smem, stream, tmQ, tmKV, out, n_seq, L,
+                               Lpad, D, heads, causal, scale_log2e, reverse));
   count_launches(1);
   return 0;
 }

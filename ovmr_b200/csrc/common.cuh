@@ -39,6 +39,30 @@ struct ProfScope {
   ~ProfScope() { if (on) prof_end(s); }
 };
 
+// Programmatic dependent launch (PDL).  The tower kernels run back to back on one stream, each a full-device
+// persistent grid; launched with the programmatic-stream-serialization attribute, the next kernel's CTAs are
+// scheduled on an SM as soon as the previous kernel's CTA there has exited, run their prologue (barrier init,
+// TMEM allocation, descriptor prefetch) and then block in pdl_wait() until the previous grid has completed and
+// its writes are visible.  A kernel launched through launch_pdl MUST call pdl_wait() before touching global
+// memory.  OVMR_PDL=0 disables the attribute (then pdl_wait() is a no-op).
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_enabled() && !profiling()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 #define OVMR_CHECK_CUDA(expr)                                                     \
   do {                                                                            \
     cudaError_t _e = (expr);                                                      \
@@ -70,6 +94,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// PDL: block until every prerequisite grid has completed and flushed (no-op without the launch attribute)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -351,13 +351,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int te = ep.reverse ? total_tiles - 1 - tile : tile;
+        const int m_blk = te / n_tiles, n_blk = te % n_tiles;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -400,9 +402,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     EpiCtx cx{stg_base + (warp - 4) * Cfg::STG_BUFS * BOX_BYTES, rbar_base + 16u * (warp - 4), 0u, 0u};
     uint32_t iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int te = ep.reverse ? total_tiles - 1 - tile : tile;
+      const int m_blk = te / n_tiles, n_blk = te % n_tiles;
       const int nxt = tile + gridDim.x;
-      const int nrow = nxt < total_tiles ? (nxt / n_tiles) * BLOCK_M : -1, ncol = (nxt % n_tiles) * BLOCK_N;
+      const int nxe = ep.reverse ? total_tiles - 1 - nxt : nxt;
+      const int nrow = nxt < total_tiles ? (nxe / n_tiles) * BLOCK_M : -1, ncol = nxt < total_tiles ? (nxe % n_tiles) * BLOCK_N : 0;
       const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
       epilogue_tile<BLOCK_N, MODE, Cfg::STG_BUFS, false>(ep, &tmC, &tmR, M, N, m_blk * BLOCK_M, n_blk * BLOCK_N, nrow, ncol,
                                                           tmem_base + as * BLOCK_N, tfull_bar(as), aphase,
@@ -496,13 +500,15 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer (both CTAs) =====================
       uint32_t stage = 0, phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-        const int m_pair = tile / n_tiles, n_blk = tile % n_tiles;
+        const int te = ep.reverse ? total_tiles - 1 - tile : tile;
+        const int m_pair = te / n_tiles, n_blk = te % n_tiles;
         const int m0 = m_pair * 2 * BLOCK_M + rank * BLOCK_M;        // this CTA's 128 rows of the 256-row tile
         const int n0 = n_blk * BLOCK_N + rank * (BLOCK_N / 2);       // this CTA's half of the weight rows
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -546,10 +552,12 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     EpiCtx cx{stg_base + (warp - 4) * Cfg::STG_BUFS * BOX_BYTES, rbar_base + 16u * (warp - 4), 0u, 0u};
     uint32_t iter = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++iter) {
-      const int m_pair = tile / n_tiles, n_blk = tile % n_tiles;
+      const int te = ep.reverse ? total_tiles - 1 - tile : tile;
+      const int m_pair = te / n_tiles, n_blk = te % n_tiles;
       const int nxt = tile + n_clusters;
-      const int nrow = nxt < total_tiles ? (nxt / n_tiles) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M : -1;
-      const int ncol = (nxt % n_tiles) * BLOCK_N;
+      const int nxe = ep.reverse ? total_tiles - 1 - nxt : nxt;
+      const int nrow = nxt < total_tiles ? (nxe / n_tiles) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M : -1;
+      const int ncol = nxt < total_tiles ? (nxe % n_tiles) * BLOCK_N : 0;
       const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
       epilogue_tile<BLOCK_N, MODE, Cfg::STG_BUFS, true>(ep, &tmC, &tmR, M, N, m_pair * 2 * BLOCK_M + rank * BLOCK_M,
                                                          n_blk * BLOCK_N, nrow, ncol, tmem_base + as * BLOCK_N,
@@ -610,8 +618,7 @@ int launch(const void* A, long long lda, const void* B, long long ldb, int M, in
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, stream);  // work = algorithmic FLOPs
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mp.a, mp.b, mp.c, mp.r, M, N, K, ep);
-  OVMR_CHECK_CUDA(cudaGetLastError());
+  OVMR_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, mp.a, mp.b, mp.c, mp.r, M, N, K, ep));
   count_launches(1);
   return 0;
 }
@@ -634,8 +641,8 @@ int launch_pair(const void* A, long long lda, const void* B, long long ldb, int 
   const int max_clusters = num_sms() / 2;
   const int clusters = total < max_clusters ? total : max_clusters;
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, stream);
-  kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mp.a, mp.b, mp.c, mp.r, M, N, K, ep);
-  OVMR_CHECK_CUDA(cudaGetLastError());
+  OVMR_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, mp.a, mp.b, mp.c, mp.r, M, N,
+                             K, ep));
   count_launches(1);
   return 0;
 }

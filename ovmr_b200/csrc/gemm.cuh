@@ -26,6 +26,8 @@ struct GemmEpilogue {
   float alpha = 1.0f;
   int row_grp = 0;
   int fp16 = 0;  // 16-bit format of A, B and of a 16-bit output: 0 = bf16, 1 = IEEE fp16
+  int reverse = 0;  // walk the output tiles last-to-first (see api.cu: alternating sweep direction keeps the
+                    // rows the previous kernel wrote last — still resident in L2 — first in line)
 };
 
 // A: 16-bit [M,K] leading dim lda (elements); B: 16-bit [N,K] leading dim ldb (format: ep.fp16).

@@ -21,10 +21,12 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, long long ldx, int rows, const int* __restrict__ gather,
                  long long gather_mul, const float* __restrict__ w, const float* __restrict__ b,
                  float* out32, long long ld32, __nv_bfloat16* __restrict__ out16, long long ld16,
-                 const float* __restrict__ w2, const float* __restrict__ b2, int fp16) {
+                 const float* __restrict__ w2, const float* __restrict__ b2, int fp16, int reverse) {
   constexpr int D = NV * 128;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (reverse) row = rows - 1 - row;  // last rows first: they are the ones the producer left in L2
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   long long src = row;
   if (gather) src = static_cast<long long>(row) * gather_mul + gather[row];
@@ -290,7 +292,7 @@ inline int grid_for(long long work_items, int threads, int max_blocks_mult = 8) 
 
 int layernorm(const float* x, long long ldx, int rows, int D, const int* gather, long long gather_mul,
               const float* w, const float* b, float* out32, long long ld32, void* out16, long long ld16,
-              const float* w2, const float* b2, int fp16, cudaStream_t stream) {
+              const float* w2, const float* b2, int fp16, cudaStream_t stream, int reverse) {
   OVMR_REQUIRE(rows > 0, "layernorm: rows=%d", rows);
   OVMR_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, "layernorm: D=%d must be a multiple of 128 in [128,1024]", D);
   OVMR_REQUIRE(out32 || out16, "layernorm: no output");
@@ -301,8 +303,8 @@ int layernorm(const float* x, long long ldx, int rows, int D, const int* gather,
   ProfScope prof(PROF_LAYERNORM, static_cast<double>(rows) * D * (4.0 + (out32 ? 4.0 : 0.0) + (out16 ? 2.0 : 0.0)), stream);
 #define LN_CASE(NV)                                                                                     \
   case NV:                                                                                              \
-    layernorm_kernel<NV><<<grid, warps * 32, 0, stream>>>(x, ldx, rows, gather, gather_mul, w, b, out32, \
-                                                          ld32, o16, ld16, w2, b2, fp16);               \
+    OVMR_CHECK_CUDA(launch_pdl(layernorm_kernel<NV>, dim3(grid), dim3(warps * 32), 0, stream, x, ldx, rows, gather, \
+                               gather_mul, w, b, out32, ld32, o16, ld16, w2, b2, fp16, reverse));        \
     break;
   switch (D / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)

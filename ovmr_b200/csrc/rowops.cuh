@@ -8,7 +8,7 @@ namespace ovmr {
 // <= 1 => identity). out32 (fp32) and/or out16 (bf16). If w2/b2 are given, out16 = LN2(LN(x)).
 int layernorm(const float* x, long long ldx, int rows, int D, const int* gather, long long gather_mul,
               const float* w, const float* b, float* out32, long long ld32, void* out16, long long ld16,
-              const float* w2, const float* b2, int fp16, cudaStream_t stream);
+              const float* w2, const float* b2, int fp16, cudaStream_t stream, int reverse = 0);
 
 int patchify(const float* images, void* out16, int B, int R, int P, int ldo, int fp16, cudaStream_t stream);
 int cls_rows(float* x, const float* cls, const float* pos, int B, int L, int D, cudaStream_t stream);

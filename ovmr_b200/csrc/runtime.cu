@@ -1,6 +1,7 @@
 // ovmr_b200 — tiny host runtime shared by all kernels: last-error string, device props.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <cudaTypedefs.h>
 
@@ -55,6 +56,14 @@ cudaEvent_t prof_event() {
 }  // namespace
 
 bool profiling() { return g_prof_on; }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("OVMR_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
 
 void prof_begin(int cat, double work, cudaStream_t s) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
