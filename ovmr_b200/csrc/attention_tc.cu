@@ -111,24 +111,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== UMMA issuer =====================
-      const uint32_t idesc_s = umma_idesc_16b_f32(QTILE, Lpad, FP16 ? 1 : 0);
-      const uint32_t idesc_o = umma_idesc_16b_f32_bmn(QTILE, 64, FP16 ? 1 : 0);
-      const int ksteps = Lpad / 16;
-      // Event-driven issue order: S of the next tile goes out as soon as its TMEM region, Q and K/V are ready;
-      // P V of the oldest pending tile goes out as soon as its softmax group has written P.  Neither waits
-      // behind the other (the two softmax groups would otherwise serialise on this thread).
-      const int my_works = (n_work - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-      const uint32_t T = static_cast<uint32_t>(my_works) * nqt;   // tiles of this CTA
-      uint32_t next_s = 0, next_pv = 0;
-      while (next_pv < T) {
-        if (next_s < T && next_s < next_pv + 2) {
-          const uint32_t t = next_s, wi = t / nqt, j = t % nqt;
-          const uint32_t r = t & 1u, n = t >> 1, qs = t & 1u, ks = wi & 1u, kn = wi >> 1;
-          if (mbar_try_wait(r_free(r), (n & 1u) ^ 1u) && mbar_try_wait(q_full(qs), n & 1u) &&
-              (j != 0 || mbar_try_wait(kv_full(ks), kn & 1u))) {
-            tc_fence_after();
+    // ===================== UMMA issuer (whole warp, converged; one elected lane issues) =====================
+    // tcgen05.mma / commit take uniform-register operands: under `if (lane == 0)` the compiler wraps each of them
+    // in a divergence loop (~100 cycles per MMA); under elect_one() they are emitted bare.
+    const uint32_t idesc_s = umma_idesc_16b_f32(QTILE, Lpad, FP16 ? 1 : 0);
+    const uint32_t idesc_o = umma_idesc_16b_f32_bmn(QTILE, 64, FP16 ? 1 : 0);
+    const int ksteps = Lpad / 16;
+    // Event-driven issue order: S of the next tile goes out as soon as its TMEM region, Q and K/V are ready;
+    // P V of the oldest pending tile goes out as soon as its softmax group has written P.  Neither waits
+    // behind the other (the two softmax groups would otherwise serialise on this warp).  When nothing is
+    // ready the warp sleeps briefly instead of spinning: it shares a scheduler with two softmax warps.
+    const int my_works = (n_work - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const uint32_t T = static_cast<uint32_t>(my_works) * nqt;   // tiles of this CTA
+    uint32_t next_s = 0, next_pv = 0;
+    while (next_pv < T) {
+      bool progress = false;
+      if (next_s < T && next_s < next_pv + 2) {
+        const uint32_t t = next_s, wi = t / nqt, j = t % nqt;
+        const uint32_t r = t & 1u, n = t >> 1, qs = t & 1u, ks = wi & 1u, kn = wi >> 1;
+        const bool ready = mbar_test(r_free(r), (n & 1u) ^ 1u) && mbar_test(q_full(qs), n & 1u) &&
+                           (j != 0 || mbar_test(kv_full(ks), kn & 1u));
+        if (__all_sync(0xffffffffu, ready)) {
+          tc_fence_after();
+          if (elect_one()) {
             const uint64_t q_desc = umma_desc_k_sw128(sQ + qs * Q_BYTES);
             const uint64_t k_desc = umma_desc_k_sw128(sK + ks * kv_stride);
 #pragma unroll
@@ -136,14 +141,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               umma_bf16_ss(tmem_base + r * 256u, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
             umma_commit(s_full(r));
             umma_commit(q_empty(qs));
-            ++next_s;
           }
+          __syncwarp();
+          ++next_s;
+          progress = true;
         }
-        if (next_pv < next_s) {
-          const uint32_t t = next_pv, wi = t / nqt, j = t % nqt;
-          const uint32_t r = t & 1u, n = t >> 1, ks = wi & 1u;
-          if (mbar_try_wait(p_full(r), n & 1u)) {
-            tc_fence_after();
+      }
+      if (next_pv < next_s) {
+        const uint32_t t = next_pv, wi = t / nqt, j = t % nqt;
+        const uint32_t r = t & 1u, n = t >> 1, ks = wi & 1u;
+        if (__all_sync(0xffffffffu, mbar_test(p_full(r), n & 1u))) {
+          tc_fence_after();
+          if (elect_one()) {
             const uint32_t region = tmem_base + r * 256u;
             const uint64_t v_desc = umma_desc_mn_sw128(sV + ks * kv_stride, kv_bytes);
             for (int kk = 0; kk < ksteps; ++kk) {
@@ -152,10 +161,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             umma_commit(o_full(r));
             if (j == static_cast<uint32_t>(nqt) - 1) umma_commit(kv_empty(ks));
-            ++next_pv;
           }
+          __syncwarp();
+          ++next_pv;
+          progress = true;
         }
       }
+      if (!progress) __nanosleep(64);
     }
   } else if (warp >= 4) {
     // ===================== softmax + output (two groups of 4 warps) =====================

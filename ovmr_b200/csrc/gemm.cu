@@ -354,35 +354,38 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int te = ep.reverse ? total_tiles - 1 - tile : tile;
-        const int m_blk = te / n_tiles, n_blk = te % n_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+    // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int te = ep.reverse ? total_tiles - 1 - tile : tile;
+      const int m_blk = te / n_tiles, n_blk = te % n_tiles;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           tma_load_2d(sa, &tmA, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
           tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== UMMA issuer =====================
-      const uint32_t idesc = umma_idesc_16b_f32(BLOCK_M, BLOCK_N, ep.fp16);
-      uint32_t stage = 0, phase = 0, iter = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-        const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
-        mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
+    // ===================== UMMA issuer (whole warp converged; one elected lane issues) =====================
+    // tcgen05.mma / commit take uniform-register operands: under `if (lane == 0)` the compiler wraps each of them in
+    // a divergence loop plus R2UR moves; under elect_one() they are emitted bare, back to back.
+    const uint32_t idesc = umma_idesc_16b_f32(BLOCK_M, BLOCK_N, ep.fp16);
+    uint32_t stage = 0, phase = 0, iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
+      mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint64_t a_desc = umma_desc_k_sw128(sa);
           const uint64_t b_desc = umma_desc_k_sw128(sa + Cfg::A_BYTES);
@@ -393,8 +396,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
           if (kb == k_blocks - 1) umma_commit(tfull_bar(as));
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= 4) {
@@ -503,28 +507,29 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer (both CTAs) =====================
-      uint32_t stage = 0, phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-        const int te = ep.reverse ? total_tiles - 1 - tile : tile;
-        const int m_pair = te / n_tiles, n_blk = te % n_tiles;
-        const int m0 = m_pair * 2 * BLOCK_M + rank * BLOCK_M;        // this CTA's 128 rows of the 256-row tile
-        const int n0 = n_blk * BLOCK_N + rank * (BLOCK_N / 2);       // this CTA's half of the weight rows
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+    // ===================== TMA producer (both CTAs; whole warp converged, one elected lane issues) =====================
+    uint32_t stage = 0, phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      const int te = ep.reverse ? total_tiles - 1 - tile : tile;
+      const int m_pair = te / n_tiles, n_blk = te % n_tiles;
+      const int m0 = m_pair * 2 * BLOCK_M + rank * BLOCK_M;        // this CTA's 128 rows of the 256-row tile
+      const int n0 = n_blk * BLOCK_N + rank * (BLOCK_N / 2);       // this CTA's half of the weight rows
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
           tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
           tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * BLOCK_K, n0);
           if (!leader) mbar_arrive_remote(full_bar(stage), 0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ===================== UMMA issuer (leader CTA only) =====================
+    if (leader) {
+      // ===================== UMMA issuer (leader CTA only; whole warp converged, one elected lane issues) ==========
       const uint32_t idesc = umma_idesc_16b_f32(2 * BLOCK_M, BLOCK_N, ep.fp16);
       uint32_t stage = 0, phase = 0, iter = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++iter) {
@@ -535,14 +540,17 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint64_t a_desc = umma_desc_k_sw128(sa);
-          const uint64_t b_desc = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+          if (elect_one()) {
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            const uint64_t a_desc = umma_desc_k_sw128(sa);
+            const uint64_t b_desc = umma_desc_k_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_16b_ss_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair_mc(empty_bar(stage), 3);          // frees this stage in both CTAs
-          if (kb == k_blocks - 1) umma_commit_pair_mc(tfull_bar(as), 3);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_16b_ss_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair_mc(empty_bar(stage), 3);          // frees this stage in both CTAs
+            if (kb == k_blocks - 1) umma_commit_pair_mc(tfull_bar(as), 3);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }

@@ -1,0 +1,28 @@
+"""Debug: per-phase clock64 trace of the tcgen05 attention kernel (build with -DOVMR_ATTN_TRACE)."""
+import sys, os, ctypes, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ovmr_b200 import _lib as L
+lib = L.lib()
+import ctypes as _c
+B, Lq, H, D = 256, 197, 12, 768
+qkv = torch.randn(B * Lq, 3 * D, device="cuda").bfloat16()
+out = torch.empty(B * Lq, D, device="cuda", dtype=torch.bfloat16)
+for _ in range(3):
+    L.check(lib.ovmr_attention(qkv.data_ptr(), out.data_ptr(), B, Lq, D, H, 0, 0, L.stream()))
+torch.cuda.synchronize()
+n = 2400
+buf = (ctypes.c_longlong * n)()
+cdll = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ovmr_b200", "libovmr_b200.so"))
+cdll.ovmr_debug_attn_trace(buf, n)
+L.check(lib.ovmr_attention(qkv.data_ptr(), out.data_ptr(), B, Lq, D, H, 0, 0, L.stream()))
+torch.cuda.synchronize()
+cdll.ovmr_debug_attn_trace(buf, n)
+names = ["S_issue", "PV_issue", "iter_start", "s_full", "pass1_done", "exp1_done", "o_full", "out_done", "exp2_done", "arrived", "S_begin", "PV_begin", "r_free_ok", "q_full_ok", "Q_load"]
+t0 = buf[2 * 40 + 4]
+for t in range(4, 10):
+    print(t, "r_free arrive per warp:", [buf[(12 + w) * 40 + t] - t0 for w in range(4, 12)])
+for t in range(4, 8):
+    for off, nm in ((0, "warp4"), (40, "warp8")):
+        print(t, nm, " ".join(f"{names[s]}={buf[(s+off)*40+t]-t0}" for s in range(2, 10)))
+for t in range(4, 4):
+    print(t, " ".join(f"{names[s]}={buf[s*40+t]-t0}" for s in range(15)))
