@@ -108,6 +108,13 @@ int ovmr_transformer_forward(const ovmr_transformer* t, float* x, int n_seq, int
 int ovmr_vit_forward(const ovmr_vit* v, const float* images, int batch, float* features, int normalize,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same, from uint8 NCHW pixels [batch,3,R,R] with the reference's ToTensor + Normalize fused into the patch
+ * load (clip/clip.py:73-80 `_transform`: ToTensor, Normalize(mean, std); Dassl's test transform,
+ * dassl/data/transforms/transforms.py:495-526): v = (u8/255 - mean[c]) / std[c] in fp32, IEEE division.
+ * mean_std is a HOST pointer to 6 floats (mean RGB, std RGB).  A quarter of the H2D bytes of the fp32 entry. */
+int ovmr_vit_forward_u8(const ovmr_vit* v, const uint8_t* images, const float* mean_std, int batch, float* features,
+                        int normalize, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Tail shared by CLIP.encode_text (clip/model.py:824-831) and TextEncoder.forward
  * (trainers/mm_classifier_one_prompt.py:82-89): x fp32 [n_seq*seq_len, W] already holds
  * embeddings + positional_embedding (see ovmr_build_text_rows); causal transformer, ln_final,
@@ -137,6 +144,10 @@ int ovmr_attention(const void* qkv, void* out, int n_seq, int seq_len, int width
 /* conv1 input as GEMM operand (clip/model.py:412-414): fp32 NCHW -> bf16 [batch*G*G, ldo]. */
 int ovmr_patchify(const float* images, void* out_16bit, int batch, int resolution, int patch, int ldo, int fp16,
                   void* stream);
+
+/* uint8 variant with ToTensor + Normalize fused (see ovmr_vit_forward_u8); mean_std = HOST pointer to 6 floats. */
+int ovmr_patchify_u8(const uint8_t* images, const float* mean_std, void* out_16bit, int batch, int resolution, int patch,
+                     int ldo, int fp16, void* stream);
 
 /* Text-tower input rows: out[(n*L+t),:] = src(n,t) + positional_embedding[t].
  *   mode 0: token_embedding[ids[n*ids_ld+t]]                       (clip/model.py:821-823)

@@ -50,6 +50,8 @@ SIGNATURES = {
     "ovmr_transformer_forward": (c_int, [C.POINTER(Transformer), c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
                                          c_void_p]),
     "ovmr_vit_forward": (c_int, [C.POINTER(Vit), c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "ovmr_vit_forward_u8": (c_int, [C.POINTER(Vit), c_void_p, C.POINTER(c_float), c_int, c_void_p, c_int, c_void_p,
+                                    c_size_t, c_void_p]),
     "ovmr_text_forward": (c_int, [C.POINTER(Text), c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
                                   c_size_t, c_void_p]),
     "ovmr_gemm_tn": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll,
@@ -58,6 +60,7 @@ SIGNATURES = {
                                c_void_p, c_ll, c_void_p, c_void_p, c_int, c_void_p]),
     "ovmr_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ovmr_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ovmr_patchify_u8": (c_int, [c_void_p, C.POINTER(c_float), c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ovmr_build_text_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_void_p]),
     "ovmr_agg_build": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -222,7 +222,8 @@ class VisionTransformer(nn.Module):
 
     def forward(self, x: torch.Tensor):
         _require_cuda(x, "VisionTransformer")
-        return self.engine(x.device).encode(x, normalize=False).type(x.dtype)
+        out = self.engine(x.device).encode(x, normalize=False)   # uint8 input = raw pixels (fused ToTensor+Normalize)
+        return out if x.dtype == torch.uint8 else out.type(x.dtype)
 
 
 class CLIP(nn.Module):

@@ -163,9 +163,31 @@ int ovmr_transformer_forward(const ovmr_transformer* t, float* x, int n_seq, int
   return run_transformer(t, x, n_seq, seq_len, causal, workspace, workspace_bytes, false, sw, S(stream));
 }
 
+static int vit_forward_impl(const ovmr_vit* v, const float* images, const uint8_t* images_u8, const float* mean_std,
+                            int batch, float* features, int normalize, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 int ovmr_vit_forward(const ovmr_vit* v, const float* images, int batch, float* features, int normalize,
                      void* workspace, size_t workspace_bytes, void* stream) {
-  OVMR_REQUIRE(v && images && features && workspace, "vit_forward: null argument");
+  OVMR_REQUIRE(images != nullptr, "vit_forward: null images");
+  return vit_forward_impl(v, images, nullptr, nullptr, batch, features, normalize, workspace, workspace_bytes, stream);
+}
+
+int ovmr_vit_forward_u8(const ovmr_vit* v, const uint8_t* images, const float* mean_std, int batch, float* features,
+                        int normalize, void* workspace, size_t workspace_bytes, void* stream) {
+  OVMR_REQUIRE(images != nullptr && mean_std != nullptr, "vit_forward_u8: null images / mean_std");
+  return vit_forward_impl(v, nullptr, images, mean_std, batch, features, normalize, workspace, workspace_bytes, stream);
+}
+
+int ovmr_patchify_u8(const uint8_t* images, const float* mean_std, void* out_16bit, int batch, int resolution, int patch,
+                     int ldo, int fp16, void* stream) {
+  return ovmr::patchify_u8(images, mean_std, out_16bit, batch, resolution, patch, ldo, fp16 != 0, S(stream));
+}
+
+static int vit_forward_impl(const ovmr_vit* v, const float* images, const uint8_t* images_u8, const float* mean_std,
+                            int batch, float* features, int normalize, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  OVMR_REQUIRE(v && (images || images_u8) && features && workspace, "vit_forward: null argument");
   OVMR_REQUIRE(batch > 0, "vit_forward: batch=%d", batch);
   OVMR_REQUIRE(v->patch > 0 && v->resolution >= v->patch, "vit_forward: bad geometry");
   RET_IF(check_transformer(&v->transformer));
@@ -191,7 +213,10 @@ int ovmr_vit_forward(const ovmr_vit* v, const float* images, int batch, float* f
   // conv1 as a GEMM over patchified pixels; epilogue adds positional_embedding[1+t] and scatters
   // patch t of image b to row b*L + 1 + t; CLS rows = class_embedding + positional_embedding[0].
   const int fp16 = v->transformer.fp16 != 0;
-  RET_IF(ovmr::patchify(images, patches, batch, v->resolution, v->patch, v->k_pad, fp16, st));
+  if (images_u8)
+    RET_IF(ovmr::patchify_u8(images_u8, mean_std, patches, batch, v->resolution, v->patch, v->k_pad, fp16, st));
+  else
+    RET_IF(ovmr::patchify(images, patches, batch, v->resolution, v->patch, v->k_pad, fp16, st));
   RET_IF(ovmr::cls_rows(x, v->class_embedding, v->positional_embedding, batch, L, D, st));
   GemmEpilogue pe;
   pe.resid = v->positional_embedding; pe.ldr = D; pe.out = x; pe.ldo = D; pe.out_bf16 = 0; pe.row_grp = G * G; pe.fp16 = fp16;

@@ -113,6 +113,52 @@ patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, 
   }
 }
 
+// uint8 variant with the reference's ToTensor + Normalize fused in (clip/clip.py:73-80): v = (u8 / 255 - mean[c]) / std[c]
+// evaluated in fp32 with IEEE division in that order, i.e. exactly the tensor the reference's transform hands to
+// encode_image, then rounded once to the 16-bit GEMM operand.  4 pixels per thread (one 32-bit load).
+struct MeanStd {
+  float mean[3], std[3];
+};
+__global__ void __launch_bounds__(256)
+patchify_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int R, int P, int G, int ldo,
+                   int fp16, MeanStd ms) {
+  const long long per_img = 3LL * R * R / 4;
+  const long long total = static_cast<long long>(B) * per_img;
+  const int used = G * P;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(t / per_img);
+    long long r = t % per_img;
+    const int xq = static_cast<int>(r % (R / 4));
+    r /= (R / 4);
+    const int y = static_cast<int>(r % R);
+    const int c = static_cast<int>(r / R);
+    const int x0 = xq * 4;
+    if (y >= used || x0 >= used) continue;
+    const uint32_t px = *reinterpret_cast<const uint32_t*>(img + ((static_cast<long long>(b) * 3 + c) * R + y) * R + x0);
+    const float mean = ms.mean[c], sd = ms.std[c];
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      v[i] = __fdiv_rn(__fdiv_rn(static_cast<float>((px >> (8 * i)) & 0xffu), 255.0f) - mean, sd);
+    const int gy = y / P, py = y % P, gx = x0 / P, pxo = x0 % P;
+    __nv_bfloat16* dst = out + (static_cast<long long>(b) * G * G + gy * G + gx) * ldo + c * P * P + py * P + pxo;
+    if (P % 4 == 0) {
+      uint2 p;
+      p.x = pack16x2(v[0], v[1], fp16);
+      p.y = pack16x2(v[2], v[3], fp16);
+      *reinterpret_cast<uint2*>(dst) = p;
+    } else {  // P % 4 == 2 (patch 14): the 4 pixels may straddle two patches
+      *reinterpret_cast<uint32_t*>(dst) = pack16x2(v[0], v[1], fp16);
+      const int x2 = x0 + 2;
+      if (x2 < used) {
+        __nv_bfloat16* d2 = out + (static_cast<long long>(b) * G * G + gy * G + x2 / P) * ldo + c * P * P + py * P + x2 % P;
+        *reinterpret_cast<uint32_t*>(d2) = pack16x2(v[2], v[3], fp16);
+      }
+    }
+  }
+}
+
 __global__ void zero_pad_cols_kernel(__nv_bfloat16* out, long long rows, int k, int ldo) {
   const int pad = ldo - k;
   const long long total = rows * pad;
@@ -332,6 +378,30 @@ int patchify(const float* images, void* out, int B, int R, int P, int ldo, int f
     const long long work = static_cast<long long>(B) * 3 * R * R / 2;
     patchify_kernel<2><<<grid_for(work, 256, 16), 256, 0, stream>>>(images, o, B, R, P, G, ldo, fp16);
   }
+  OVMR_CHECK_CUDA(cudaGetLastError());
+  count_launches(1);
+  return 0;
+}
+
+int patchify_u8(const uint8_t* images, const float* mean_std, void* out, int B, int R, int P, int ldo, int fp16,
+                cudaStream_t stream) {
+  OVMR_REQUIRE(B > 0 && P > 0 && R >= P && P % 2 == 0 && R % 4 == 0, "patchify_u8: bad geometry B=%d R=%d P=%d", B, R, P);
+  OVMR_REQUIRE(mean_std != nullptr, "patchify_u8: mean/std required");
+  OVMR_REQUIRE((reinterpret_cast<uintptr_t>(images) & 3) == 0, "patchify_u8: images must be 4-byte aligned");
+  const int G = R / P, K = 3 * P * P;
+  OVMR_REQUIRE(ldo >= K && ldo % 8 == 0, "patchify_u8: ldo=%d must be >= %d and a multiple of 8", ldo, K);
+  MeanStd ms;
+  for (int i = 0; i < 3; ++i) {
+    ms.mean[i] = mean_std[i];
+    ms.std[i] = mean_std[3 + i];
+    OVMR_REQUIRE(ms.std[i] > 0.f, "patchify_u8: std[%d] must be positive", i);
+  }
+  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+  const long long rows = static_cast<long long>(B) * G * G;
+  ProfScope prof(PROF_ROWOPS, static_cast<double>(B) * 3 * R * R * 1.0 + static_cast<double>(rows) * ldo * 2.0, stream);
+  if (ldo > K) zero_pad_cols_kernel<<<grid_for(rows * (ldo - K), 256), 256, 0, stream>>>(o, rows, K, ldo);
+  const long long work = static_cast<long long>(B) * 3 * R * R / 4;
+  patchify_u8_kernel<<<grid_for(work, 256, 16), 256, 0, stream>>>(images, o, B, R, P, G, ldo, fp16, ms);
   OVMR_CHECK_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;

@@ -1,6 +1,7 @@
 // ovmr_b200 — host launchers of the HBM-bound row kernels (see rowops.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace ovmr {
 
@@ -11,6 +12,9 @@ int layernorm(const float* x, long long ldx, int rows, int D, const int* gather,
               const float* w2, const float* b2, int fp16, cudaStream_t stream, int reverse = 0);
 
 int patchify(const float* images, void* out16, int B, int R, int P, int ldo, int fp16, cudaStream_t stream);
+// uint8 NCHW images with ToTensor + Normalize(mean_std[0..3), mean_std[3..6)) fused (host pointer to 6 floats)
+int patchify_u8(const uint8_t* images, const float* mean_std, void* out16, int B, int R, int P, int ldo, int fp16,
+                cudaStream_t stream);
 int cls_rows(float* x, const float* cls, const float* pos, int B, int L, int D, cudaStream_t stream);
 int build_text_rows(float* out, const float* table, const float* pos, const int* ids, int ids_ld,
                     const int* label, const float* vtok, int n_ctx, int N, int L, int src_L, int W, int mode,

@@ -1,14 +1,20 @@
 """Host -> device staging for the evaluation loops (the reference's DataLoader(pin_memory) + `.to(device)`
 at dassl/engine/trainer.py:519-520, made asynchronous): batches are copied from pinned host memory on a
-side stream one batch ahead of the compute stream, so H2D traffic overlaps the encoders."""
-from typing import Dict, Iterable, Iterator
+side stream `depth` batches ahead of the compute stream, so H2D traffic overlaps the encoders.
+
+Image tensors land in a fixed ring of device buffers owned by the prefetcher (no allocation, no cross-stream
+allocator traffic in the loop): slot i % R is refilled only after the compute stream has passed the point
+where the batch that previously lived there was handed back (an event recorded when the NEXT batch is yielded).
+"""
+from typing import Dict, Iterable, Iterator, List
 
 import torch
 
 
 class DevicePrefetcher:
     """Wraps an iterable of {"img": Tensor | [Tensor], "label": Tensor, ...} batches (host tensors, ideally
-    pinned) and yields the same dicts with device tensors, prefetching `depth` batches ahead."""
+    pinned) and yields the same dicts with device tensors, prefetching `depth` batches ahead.  The yielded image
+    tensors are views into the ring and stay valid until `depth + 1` further batches have been requested."""
 
     def __init__(self, batches: Iterable[Dict], device, depth: int = 2):
         self.batches = batches
@@ -16,43 +22,66 @@ class DevicePrefetcher:
         self.depth = max(1, depth)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.h2d_bytes = 0
+        self._ring: Dict[str, List[torch.Tensor]] = {}
+        self._slots = self.depth + 2
+        self._released = [None] * self._slots     # compute-stream events: slot may be overwritten after this
 
-    def _stage(self, batch: Dict):
+    def _into_ring(self, key: str, slot: int, t: torch.Tensor) -> torch.Tensor:
+        """Copy a host tensor into this key's ring slot (grown to the largest batch seen)."""
+        n = t.numel()
+        ring = self._ring.setdefault(key, [None] * self._slots)
+        buf = ring[slot]
+        if buf is None or buf.dtype != t.dtype or buf.numel() < n:
+            buf = torch.empty(n, dtype=t.dtype, device=self.device)
+            ring[slot] = buf
+        dst = buf[:n].view(t.shape)
+        dst.copy_(t, non_blocking=True)
+        self.h2d_bytes += n * t.element_size()
+        return dst
+
+    def _stage(self, batch: Dict, slot: int):
         out = {}
+        rel = self._released[slot]
+        if rel is not None:
+            self.copy_stream.wait_event(rel)
         with torch.cuda.stream(self.copy_stream):
             for k, v in batch.items():
                 if isinstance(v, torch.Tensor):
-                    out[k] = v.to(self.device, non_blocking=True)
-                    if v.device.type == "cpu":
-                        self.h2d_bytes += v.numel() * v.element_size()
+                    out[k] = self._into_ring(k, slot, v) if v.device.type == "cpu" else v.to(self.device)
                 elif isinstance(v, (list, tuple)) and v and isinstance(v[0], torch.Tensor):
-                    out[k] = [t.to(self.device, non_blocking=True) for t in v]
-                    self.h2d_bytes += sum(t.numel() * t.element_size() for t in v if t.device.type == "cpu")
+                    out[k] = [self._into_ring(f"{k}.{i}", slot, t) if t.device.type == "cpu" else t.to(self.device)
+                              for i, t in enumerate(v)]
                 else:
                     out[k] = v
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        return out, ev
+        return out, ev, slot
 
     def __iter__(self) -> Iterator[Dict]:
         queue = []
-        it = iter(self.batches)
         cur = torch.cuda.current_stream(self.device)
-        for batch in it:
-            queue.append(self._stage(batch))
-            if len(queue) > self.depth:
-                out, ev = queue.pop(0)
-                cur.wait_event(ev)
-                for v in out.values():
-                    for t in (v if isinstance(v, list) else [v]):
-                        if isinstance(t, torch.Tensor) and t.is_cuda:
-                            t.record_stream(cur)
-                yield out
-        while queue:
-            out, ev = queue.pop(0)
+        prev_slot = None
+
+        def hand_over(item):
+            nonlocal prev_slot
+            out, ev, slot = item
+            if prev_slot is not None:     # the consumer is done with the previous batch: its slot may be refilled
+                rel = torch.cuda.Event()
+                rel.record(cur)
+                self._released[prev_slot] = rel
+            prev_slot = slot
             cur.wait_event(ev)
-            for v in out.values():
-                for t in (v if isinstance(v, list) else [v]):
-                    if isinstance(t, torch.Tensor) and t.is_cuda:
-                        t.record_stream(cur)
-            yield out
+            return out
+
+        i = 0
+        for batch in self.batches:
+            queue.append(self._stage(batch, i % self._slots))
+            i += 1
+            if len(queue) > self.depth:
+                yield hand_over(queue.pop(0))
+        while queue:
+            yield hand_over(queue.pop(0))
+        if prev_slot is not None:
+            rel = torch.cuda.Event()
+            rel.record(cur)
+            self._released[prev_slot] = rel

@@ -105,25 +105,40 @@ class VisionEngine:
                             k_["proj_t"].data_ptr(), self.t.struct)
         self.ws = Workspace(device)
 
-    def encode(self, images: torch.Tensor, normalize: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """images fp32 NCHW on the device -> fp32 [B, E] (optionally L2-normalised)."""
+    # CLIP's preprocessing constants (clip/clip.py:79); used when uint8 pixels are passed to encode()
+    CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+    CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+    def encode(self, images: torch.Tensor, normalize: bool = False, out: Optional[torch.Tensor] = None,
+               mean=None, std=None) -> torch.Tensor:
+        """images NCHW on the device -> fp32 [B, E] (optionally L2-normalised).  float images are taken as already
+        normalised (what the reference's transform produces); uint8 images are raw pixels and get ToTensor +
+        Normalize(mean, std) (default: CLIP's constants) fused into the patch load."""
         lib = L.lib()
         if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != self.res or images.shape[3] != self.res:
             raise ValueError(f"expected images [B,3,{self.res},{self.res}], got {tuple(images.shape)}")
         if images.device.type != "cuda":
             raise L.OvmrNativeError("ovmr_b200: images must be on the CUDA device (no CPU path)")
-        images = images.to(F32).contiguous()
+        u8 = images.dtype == torch.uint8
+        images = images.contiguous() if u8 else images.to(F32).contiguous()
         B = images.shape[0]
         feats = out if out is not None else torch.empty(B, self.embed_dim, dtype=F32, device=images.device)
         if B == 0:
             return feats
         mb = min(self.max_batch, B)
         buf = self.ws.get(lib.ovmr_vit_workspace_bytes(C.byref(self.struct), mb))
+        if u8:
+            ms = (C.c_float * 6)(*(tuple(mean or self.CLIP_MEAN) + tuple(std or self.CLIP_STD)))
         for b0 in range(0, B, mb):
             nb = min(mb, B - b0)
-            L.check(lib.ovmr_vit_forward(C.byref(self.struct), images[b0:b0 + nb].data_ptr(), nb,
-                                         feats[b0:b0 + nb].data_ptr(), int(normalize), buf.data_ptr(), buf.numel(),
-                                         L.stream()), "ovmr_vit_forward")
+            if u8:
+                L.check(lib.ovmr_vit_forward_u8(C.byref(self.struct), images[b0:b0 + nb].data_ptr(), ms, nb,
+                                                feats[b0:b0 + nb].data_ptr(), int(normalize), buf.data_ptr(),
+                                                buf.numel(), L.stream()), "ovmr_vit_forward_u8")
+            else:
+                L.check(lib.ovmr_vit_forward(C.byref(self.struct), images[b0:b0 + nb].data_ptr(), nb,
+                                             feats[b0:b0 + nb].data_ptr(), int(normalize), buf.data_ptr(), buf.numel(),
+                                             L.stream()), "ovmr_vit_forward")
         return feats
 
 

@@ -156,6 +156,31 @@ def test_patchify(B, R, P):
     assert (out.cpu()[:, k:] == 0).all()
 
 
+@pytest.mark.parametrize("B,R,P", [(3, 64, 16), (2, 224, 16), (2, 224, 14), (1, 224, 32)])
+def test_patchify_u8_matches_totensor_normalize_bit_exact(B, R, P):
+    """uint8 entry: ToTensor (/255) + Normalize ((x-mean)/std) in fp32 exactly as torchvision evaluates them
+    (clip/clip.py:73-80), then one rounding to bf16 — bit-identical to patchify of the reference's fp32 tensor."""
+    import ctypes as C
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(B + R + P)
+    u8 = torch.randint(0, 256, (B, 3, R, R), generator=g, dtype=torch.uint8)
+    mean = torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(1, 3, 1, 1)
+    std = torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(1, 3, 1, 1)
+    img = u8.float().div(255).sub(mean).div(std)        # ToTensor + Normalize, fp32
+    G = R // P
+    k = 3 * P * P
+    kpad = (k + 7) // 8 * 8
+    crop = img[:, :, :G * P, :G * P]
+    ref = crop.reshape(B, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(B * G * G, k).bfloat16()
+    out = torch.full((B * G * G, kpad), 7.0, dtype=torch.bfloat16, device=DEV)
+    ms = (C.c_float * 6)(*(mean.flatten().tolist() + std.flatten().tolist()))
+    U8 = u8.to(DEV)
+    L.check(lib.ovmr_patchify_u8(U8.data_ptr(), ms, out.data_ptr(), B, R, P, kpad, 0, L.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu()[:, :k], ref)
+    assert (out.cpu()[:, k:] == 0).all()
+
+
 def test_l2norm_split_mean():
     L, lib = _lib()
     g = torch.Generator().manual_seed(3)

@@ -68,6 +68,23 @@ def test_encode_image_and_text_match_oracle(tiny):
     assert (li.float().cpu() - ref_li).abs().max() < 1e-2 and torch.equal(lt, li.t())
 
 
+def test_encode_image_uint8_equals_float_path(tiny):
+    """encode_image on raw uint8 pixels == encode_image on the reference transform's fp32 tensor (bit-exact: the
+    fused ToTensor+Normalize produces the same 16-bit patch operand)."""
+    from ovmr_b200.engine import VisionEngine
+    model = tiny.model.image_encoder
+    res = model.input_resolution
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (5, 3, res, res), generator=g, dtype=torch.uint8)
+    mean = torch.tensor(VisionEngine.CLIP_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(VisionEngine.CLIP_STD).view(1, 3, 1, 1)
+    f32 = u8.float().div(255).sub(mean).div(std)
+    eng = model.engine(torch.device(DEV))
+    a = eng.encode(u8.to(DEV), normalize=True)
+    b = eng.encode(f32.to(DEV), normalize=True)
+    assert torch.equal(a, b)
+
+
 def test_text_encoder_and_prompt_learner_api(tiny):
     """TextEncoder.forward(prompts, eos_index) and PromptLearner.forward's 5-tuple (reference call contract)."""
     pl_mod = tiny.model.prompt_learner
