@@ -34,7 +34,7 @@ extern "C" {
 
 #define OVMR_OK 0
 #define OVMR_ERR_INVALID 10001
-#define OVMR_ABI_VERSION 1
+#define OVMR_ABI_VERSION 2
 
 /* ---------------------------------------------------------------- introspection */
 int ovmr_abi_version(void);
@@ -59,6 +59,13 @@ typedef struct ovmr_block_weights {
   const float* ln2_w;  const float* ln2_b;      /* ln_2.*                              [D]      */
   const void*  fc_w;   const float* fc_b;       /* mlp.c_fc.weight bf16 [4D,D] / bias [4D]     */
   const void*  proj_w; const float* proj_b;     /* mlp.c_proj.weight bf16 [D,4D] / bias [D]    */
+  /* Optional LayerNorm folding (all six NULL = ln_1 / ln_2 run as kernels).  With them set, the block never
+   * materialises LN(x): the residual GEMMs also emit a 16-bit copy of x and per-row (sum, sum of squares), and
+   * the QKV / c_fc GEMMs run on the RAW rows with gamma folded into the weights,
+   *   y = rstd * (x16 . W'^T - mean * colsum) + bias',   W' = W * gamma (16-bit), colsum[n] = sum_k W'[n,k] (fp32),
+   *   bias'[n] = b[n] + sum_k beta[k] * W[n,k] (fp32) — algebraically LN(x) . W^T + b (clip/model.py:191-194). */
+  const void*  qkv_wf; const float* qkv_cs; const float* qkv_bf;   /* [3D,D] 16-bit, [3D], [3D] */
+  const void*  fc_wf;  const float* fc_cs;  const float* fc_bf;    /* [4D,D] 16-bit, [4D], [4D] */
 } ovmr_block_weights;
 
 /* Transformer / TransformerDropout (clip/model.py:261-269, 341-350). `blocks` is a HOST array. */

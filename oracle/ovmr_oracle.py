@@ -322,6 +322,25 @@ def zero_shot_classifier(sd: State, tokenized_prompts: Tensor) -> Tensor:
     return torch.stack(outs)
 
 
+def template_ensemble_classifier(sd: State, token_sets: Sequence[Tensor]) -> Tensor:
+    """ZeroshotCLIP2.build_model (trainers/zsclip.py:88-96): token_sets[t] = tokenised prompts of template t for all
+    classes [C, 77]; per template encode_text + L2 norm, mean over templates, L2 norm.  One template =
+    ZeroshotCLIP (:45-50)."""
+    mean = 0
+    for tok in token_sets:
+        f = encode_text(sd, tok)
+        mean = mean + f / f.norm(dim=-1, keepdim=True)
+    mean = mean / len(token_sets)
+    return mean / mean.norm(dim=-1, keepdim=True)
+
+
+def zeroshot_logits(sd: State, images: Tensor, text_features: Tensor) -> Tensor:
+    """ZeroshotCLIP.model_inference (trainers/zsclip.py:54-59)."""
+    f = encode_image(sd, images)
+    f = f / f.norm(dim=-1, keepdim=True)
+    return sd["logit_scale"].exp() * f @ text_features.t()
+
+
 # --------------------------------------------------------------------------------------
 # Visual token generator + classifier generation
 # --------------------------------------------------------------------------------------

@@ -16,7 +16,8 @@ c_void_p, c_int, c_ll, c_float, c_size_t = C.c_void_p, C.c_int, C.c_longlong, C.
 
 class BlockWeights(C.Structure):
     _fields_ = [(n, c_void_p) for n in (
-        "ln1_w", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_w", "ln2_b", "fc_w", "fc_b", "proj_w", "proj_b")]
+        "ln1_w", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_w", "ln2_b", "fc_w", "fc_b", "proj_w", "proj_b",
+        "qkv_wf", "qkv_cs", "qkv_bf", "fc_wf", "fc_cs", "fc_bf")]
 
 
 class Transformer(C.Structure):
@@ -96,7 +97,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = res
         fn.argtypes = args
-    if lib.ovmr_abi_version() != 1:
+    if lib.ovmr_abi_version() != 2:
         raise OvmrNativeError("libovmr_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

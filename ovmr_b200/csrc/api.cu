@@ -27,6 +27,8 @@ inline size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255);
 struct TransformerWs {
   void* a_bf16;    // [rows, D]   LayerNorm output / attention output (GEMM A operands)
   void* big_bf16;  // [rows, 4D]  QKV (3D) and MLP hidden (4D), never live together
+  void* x16;       // [rows, D]   folded LayerNorm: 16-bit copy of the residual stream (raw A operand of QKV / c_fc)
+  float2* stats[2];  // [rows, D/64] per-slab (sum, sum of squares) of the residual rows: [0] feeds QKV, [1] feeds c_fc
   size_t bytes;
 };
 
@@ -35,10 +37,18 @@ TransformerWs carve_transformer_ws(void* base, long long rows, int width) {
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   const size_t a = align256(static_cast<size_t>(rows) * width * 2);
   const size_t b = align256(static_cast<size_t>(rows) * width * 4 * 2);
+  const size_t st = align256(static_cast<size_t>(rows) * (width / 64) * sizeof(float2));
   w.a_bf16 = p;
   w.big_bf16 = p + a;
-  w.bytes = a + b;
+  w.x16 = p + a + b;
+  w.stats[0] = reinterpret_cast<float2*>(p + a + b + a);
+  w.stats[1] = reinterpret_cast<float2*>(p + a + b + a + st);
+  w.bytes = a + b + a + 2 * st;
   return w;
+}
+
+inline bool folded(const ovmr_block_weights& bw) {
+  return bw.qkv_wf && bw.qkv_cs && bw.qkv_bf && bw.fc_wf && bw.fc_cs && bw.fc_bf;
 }
 
 // Alternating sweep direction.  Every kernel of a tower streams over the same token rows; an activation of a
@@ -78,34 +88,61 @@ int check_transformer(const ovmr_transformer* t) {
 }
 
 // One pre-LN residual block on the fp32 residual stream x [rows, D] (clip/model.py:191-194).
+// fold: LayerNorm folding (include/ovmr_b200.h): on entry ws.x16 / ws.stats[0] describe x; emit_next = the block's
+// last GEMM leaves them describing the new x (false for the tower's last block).
 int run_block(const ovmr_block_weights& bw, float* x, int n_seq, int seq_len, int D, int heads, int causal,
-              int fp16, const TransformerWs& ws, bool ln1_done, Sweep& sw, cudaStream_t st) {
+              int fp16, const TransformerWs& ws, bool ln1_done, bool fold, bool emit_next, Sweep& sw, cudaStream_t st) {
   const int rows = n_seq * seq_len;
+  const int parts = D / 64;
   // x + attn(ln_1(x))
-  if (!ln1_done)
+  if (!fold && !ln1_done)
     RET_IF(ovmr::layernorm(x, D, rows, D, nullptr, 0, bw.ln1_w, bw.ln1_b, nullptr, 0, ws.a_bf16, D, nullptr, nullptr, fp16, st,
                            sw.next()));
   GemmEpilogue qkv;
-  qkv.bias = bw.qkv_b; qkv.out = ws.big_bf16; qkv.ldo = 3LL * D; qkv.out_bf16 = 1; qkv.fp16 = fp16; qkv.reverse = sw.next();
-  RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.qkv_w, D, rows, 3 * D, D, qkv, st));
+  qkv.out = ws.big_bf16; qkv.ldo = 3LL * D; qkv.out_bf16 = 1; qkv.fp16 = fp16; qkv.reverse = sw.next();
+  if (fold) {
+    qkv.bias = bw.qkv_bf; qkv.stats_in = ws.stats[0]; qkv.stats_parts = parts; qkv.ln_width = D; qkv.colsum = bw.qkv_cs;
+    RET_IF(ovmr::gemm_tn(ws.x16, D, bw.qkv_wf, D, rows, 3 * D, D, qkv, st));
+  } else {
+    qkv.bias = bw.qkv_b;
+    RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.qkv_w, D, rows, 3 * D, D, qkv, st));
+  }
   RET_IF(ovmr::attention(ws.big_bf16, ws.a_bf16, n_seq, seq_len, D, heads, causal, fp16, st, sw.next()));
   GemmEpilogue op;
   op.bias = bw.out_b; op.resid = x; op.ldr = D; op.out = x; op.ldo = D; op.out_bf16 = 0; op.fp16 = fp16; op.reverse = sw.next();
+  if (fold) { op.out16 = ws.x16; op.ld16 = D; op.stats_out = ws.stats[1]; }
   RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.out_w, D, rows, D, D, op, st));
   // x + c_proj(QuickGELU(c_fc(ln_2(x))))
-  RET_IF(ovmr::layernorm(x, D, rows, D, nullptr, 0, bw.ln2_w, bw.ln2_b, nullptr, 0, ws.a_bf16, D, nullptr, nullptr, fp16, st,
-                         sw.next()));
+  if (!fold)
+    RET_IF(ovmr::layernorm(x, D, rows, D, nullptr, 0, bw.ln2_w, bw.ln2_b, nullptr, 0, ws.a_bf16, D, nullptr, nullptr, fp16, st,
+                           sw.next()));
   GemmEpilogue fc;
-  fc.bias = bw.fc_b; fc.out = ws.big_bf16; fc.ldo = 4LL * D; fc.out_bf16 = 1; fc.act = 1; fc.fp16 = fp16; fc.reverse = sw.next();
-  RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.fc_w, D, rows, 4 * D, D, fc, st));
+  fc.out = ws.big_bf16; fc.ldo = 4LL * D; fc.out_bf16 = 1; fc.act = 1; fc.fp16 = fp16; fc.reverse = sw.next();
+  if (fold) {
+    fc.bias = bw.fc_bf; fc.stats_in = ws.stats[1]; fc.stats_parts = parts; fc.ln_width = D; fc.colsum = bw.fc_cs;
+    RET_IF(ovmr::gemm_tn(ws.x16, D, bw.fc_wf, D, rows, 4 * D, D, fc, st));
+  } else {
+    fc.bias = bw.fc_b;
+    RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.fc_w, D, rows, 4 * D, D, fc, st));
+  }
   GemmEpilogue pj;
   pj.bias = bw.proj_b; pj.resid = x; pj.ldr = D; pj.out = x; pj.ldo = D; pj.out_bf16 = 0; pj.fp16 = fp16; pj.reverse = sw.next();
+  if (fold && emit_next) { pj.out16 = ws.x16; pj.ld16 = D; pj.stats_out = ws.stats[0]; }
   RET_IF(ovmr::gemm_tn(ws.big_bf16, 4LL * D, bw.proj_w, 4LL * D, rows, D, 4 * D, pj, st));
   return 0;
 }
 
+// Folding applies to the whole tower or not at all (every block must carry the folded operands).
+bool tower_folded(const ovmr_transformer* t) {
+  for (int l = 0; l < t->layers; ++l)
+    if (!folded(t->blocks[l])) return false;
+  return true;
+}
+
 int run_transformer(const ovmr_transformer* t, float* x, int n_seq, int seq_len, int causal, void* wsp,
                     size_t ws_bytes, bool first_ln1_done, Sweep& sw, cudaStream_t st) {
+  // first_ln1_done: the caller has prepared layer 0's input — ws.a_bf16 = ln_1(x) (unfolded towers) or
+  // ws.x16 / ws.stats[0] describing x (folded towers)
   RET_IF(check_transformer(t));
   OVMR_REQUIRE(n_seq > 0 && seq_len > 0, "transformer: empty input (n_seq=%d seq_len=%d)", n_seq, seq_len);
   const long long rows = static_cast<long long>(n_seq) * seq_len;
@@ -113,9 +150,13 @@ int run_transformer(const ovmr_transformer* t, float* x, int n_seq, int seq_len,
   OVMR_REQUIRE(wsp != nullptr && ws_bytes >= ovmr_transformer_workspace_bytes(rows, t->width),
                "transformer: workspace too small (%zu < %zu)", ws_bytes, ovmr_transformer_workspace_bytes(rows, t->width));
   const TransformerWs ws = carve_transformer_ws(wsp, rows, t->width);
+  const bool fold = tower_folded(t);
+  if (fold && !first_ln1_done)   // 16-bit copy + row statistics of the incoming x (identity LayerNorm pass)
+    RET_IF(ovmr::layernorm(x, t->width, static_cast<int>(rows), t->width, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, 0,
+                           nullptr, nullptr, t->fp16 != 0, st, sw.next(), ws.x16, t->width, ws.stats[0], t->width / 64));
   for (int l = 0; l < t->layers; ++l) {
     RET_IF(run_block(t->blocks[l], x, n_seq, seq_len, t->width, t->heads, causal, t->fp16 != 0, ws,
-                     l == 0 && first_ln1_done, sw, st));
+                     l == 0 && first_ln1_done, fold, l + 1 < t->layers, sw, st));
   }
   return 0;
 }
@@ -137,7 +178,8 @@ int ovmr_profile_summary(double* ms, double* work, long long* launches, int ncat
 }
 
 size_t ovmr_transformer_workspace_bytes(long long rows, int width) {
-  return align256(static_cast<size_t>(rows) * width * 2) + align256(static_cast<size_t>(rows) * width * 8);
+  return 2 * align256(static_cast<size_t>(rows) * width * 2) + align256(static_cast<size_t>(rows) * width * 8) +
+         2 * align256(static_cast<size_t>(rows) * (width / 64) * sizeof(float2));
 }
 
 size_t ovmr_vit_workspace_bytes(const ovmr_vit* v, int batch) {
@@ -226,8 +268,12 @@ static int vit_forward_impl(const ovmr_vit* v, const float* images, const uint8_
   RET_IF(ovmr::gemm_tn(patches, v->k_pad, v->conv_w, v->k_pad, batch * G * G, D, v->k_pad, pe, st));
   // ln_pre (fp32, in place) chained with layer 0's ln_1 (bf16 operand of the first QKV GEMM)
   const ovmr_block_weights& b0 = v->transformer.blocks[0];
-  RET_IF(ovmr::layernorm(x, D, static_cast<int>(rows), D, nullptr, 0, v->ln_pre_w, v->ln_pre_b, x, D, ws.a_bf16, D,
-                         b0.ln1_w, b0.ln1_b, fp16, st, sw.next()));
+  if (tower_folded(&v->transformer))   // ln_pre in place + 16-bit copy / row statistics for layer 0's folded ln_1
+    RET_IF(ovmr::layernorm(x, D, static_cast<int>(rows), D, nullptr, 0, v->ln_pre_w, v->ln_pre_b, x, D, nullptr, 0, nullptr,
+                           nullptr, fp16, st, sw.next(), ws.x16, D, ws.stats[0], D / 64));
+  else
+    RET_IF(ovmr::layernorm(x, D, static_cast<int>(rows), D, nullptr, 0, v->ln_pre_w, v->ln_pre_b, x, D, ws.a_bf16, D,
+                           b0.ln1_w, b0.ln1_b, fp16, st, sw.next()));
   RET_IF(run_transformer(&v->transformer, x, batch, L, 0, tws, tws_bytes, true, sw, st));
   // ln_post on the CLS rows, projection, optional L2 normalisation
   RET_IF(ovmr::layernorm(x, D, batch, D, nullptr, L, v->ln_post_w, v->ln_post_b, nullptr, 0, cls_bf16, D, nullptr,

@@ -41,7 +41,7 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;         // 4 control warps + 8 epilogue warps
 constexpr uint32_t BOX_BYTES = 32 * 128;  // one epilogue staging box: 32 rows x 128 B
 
-enum EpiMode { EPI_GENERIC = 0, EPI_16 = 1, EPI_16_GELU = 2, EPI_F32_RESID = 3 };
+enum EpiMode { EPI_GENERIC = 0, EPI_16 = 1, EPI_16_GELU = 2, EPI_F32_RESID = 3, EPI_F32_RESID_EMIT = 4 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
   // x * sigmoid(1.702 x) with sigmoid(y) = 0.5 + 0.5 tanh(y/2): one MUFU op per element
@@ -53,6 +53,7 @@ __device__ __forceinline__ float quick_gelu(float x) {
 
 // per-warp epilogue bookkeeping
 struct EpiCtx {
+  uint32_t stg16;   // EPI_F32_RESID_EMIT: this warp's 16-bit staging box (4 KB, 1024-B aligned)
   uint32_t stg;     // this warp's staging boxes (STG_BUFS x 4 KB, 1024-B aligned)
   uint32_t rbar;    // this warp's two residual-load mbarriers
   uint32_t n_use;   // staging boxes consumed so far (box k lives in buffer k % STG_BUFS)
@@ -74,9 +75,10 @@ __device__ __forceinline__ void release_accumulator(uint32_t tempty, int lane) {
 // EPI_16 / EPI_16_GELU: this warp's 32 rows x HALF_N columns, 64 columns (one 128-B box row) at a time.
 // ---------------------------------------------------------------------------------------------
 template <int HALF_N, bool GELU, int STG_BUFS, bool PAIR>
-__device__ __forceinline__ void epilogue_16(const GemmEpilogue& ep, const CUtensorMap* tmC, int N, int row0, int col0,
-                                            uint32_t taddr, uint32_t tempty, EpiCtx& cx, int lane) {
+__device__ __forceinline__ void epilogue_16(const GemmEpilogue& ep, const CUtensorMap* tmC, int M, int N, int row0, int col0,
+                                            uint32_t taddr, uint32_t tempty, EpiCtx& cx, int lane, float ln_a, float ln_b) {
   constexpr int CHUNKS = HALF_N / 64;
+  const bool ln = ep.stats_in != nullptr;   // folded LayerNorm: out = ln_a * acc + ln_b * colsum[n] + bias[n]
 #pragma unroll 1
   for (int c = 0; c < CHUNKS; ++c) {
     const int n0 = col0 + 64 * c;
@@ -100,10 +102,19 @@ __device__ __forceinline__ void epilogue_16(const GemmEpilogue& ep, const CUtens
         b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
         b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
       }
-      x[0] = __uint_as_float(v[8 * j + 0]) + b0.x; x[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
-      x[2] = __uint_as_float(v[8 * j + 2]) + b0.z; x[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
-      x[4] = __uint_as_float(v[8 * j + 4]) + b1.x; x[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
-      x[6] = __uint_as_float(v[8 * j + 6]) + b1.z; x[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
+      if (ln) {
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+        if (n + 8 <= N) {
+          c0 = __ldg(reinterpret_cast<const float4*>(ep.colsum + n));
+          c1 = __ldg(reinterpret_cast<const float4*>(ep.colsum + n + 4));
+        }
+        b0.x = fmaf(ln_b, c0.x, b0.x); b0.y = fmaf(ln_b, c0.y, b0.y); b0.z = fmaf(ln_b, c0.z, b0.z); b0.w = fmaf(ln_b, c0.w, b0.w);
+        b1.x = fmaf(ln_b, c1.x, b1.x); b1.y = fmaf(ln_b, c1.y, b1.y); b1.z = fmaf(ln_b, c1.z, b1.z); b1.w = fmaf(ln_b, c1.w, b1.w);
+      }
+      x[0] = fmaf(ln_a, __uint_as_float(v[8 * j + 0]), b0.x); x[1] = fmaf(ln_a, __uint_as_float(v[8 * j + 1]), b0.y);
+      x[2] = fmaf(ln_a, __uint_as_float(v[8 * j + 2]), b0.z); x[3] = fmaf(ln_a, __uint_as_float(v[8 * j + 3]), b0.w);
+      x[4] = fmaf(ln_a, __uint_as_float(v[8 * j + 4]), b1.x); x[5] = fmaf(ln_a, __uint_as_float(v[8 * j + 5]), b1.y);
+      x[6] = fmaf(ln_a, __uint_as_float(v[8 * j + 6]), b1.z); x[7] = fmaf(ln_a, __uint_as_float(v[8 * j + 7]), b1.w);
       if (GELU) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) x[e] = quick_gelu(x[e]);
@@ -137,11 +148,12 @@ __device__ __forceinline__ void resid_issue_load(const CUtensorMap* tmR, int N, 
   ++cx.n_load;
 }
 
-template <int HALF_N, int STG_BUFS, bool PAIR>
+template <int HALF_N, int STG_BUFS, bool PAIR, bool EMIT>
 __device__ __forceinline__ void epilogue_f32_resid(const GemmEpilogue& ep, const CUtensorMap* tmC, const CUtensorMap* tmR,
-                                                   int N, int row0, int col0, uint32_t taddr, uint32_t tempty,
-                                                   EpiCtx& cx, int lane) {
+                                                   const CUtensorMap* tmC16, int M, int N, int row0, int col0,
+                                                   uint32_t taddr, uint32_t tempty, EpiCtx& cx, int lane) {
   constexpr int CHUNKS = HALF_N / 32;
+  float st_s = 0.f, st_q = 0.f;   // EMIT: partial (sum, sum of squares) of this row over the current 64-column slab
   // (the residual box of chunk 0 was requested by epilogue_tile before the accumulator was ready)
 #pragma unroll 1
   for (int c = 0; c < CHUNKS; ++c) {
@@ -154,26 +166,54 @@ __device__ __forceinline__ void epilogue_f32_resid(const GemmEpilogue& ep, const
     if (c == CHUNKS - 1) release_accumulator<PAIR>(tempty, lane);
     if (n0 >= N) continue;
     const uint32_t buf = cx.stg + (cx.n_use % STG_BUFS) * BOX_BYTES;
+    if (EMIT && (c & 1) == 0 && c > 0) {
+      // the 16-bit box is refilled from here on: its previous TMA store must have read it
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+    }
     mbar_wait(cx.rbar + 8u * (cx.n_use & 1u), (cx.n_use >> 1) & 1u);  // residual box has landed
     ++cx.n_use;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {  // 4 columns -> one 16-B chunk
-      const int n = n0 + 4 * j;
-      const uint32_t a = buf + lane * 128 + ((j ^ (lane & 7)) << 4);
-      float4 r;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory");
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ep.bias && n + 4 <= N) b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-      r.x += __uint_as_float(v[4 * j + 0]) + b.x;
-      r.y += __uint_as_float(v[4 * j + 1]) + b.y;
-      r.z += __uint_as_float(v[4 * j + 2]) + b.z;
-      r.w += __uint_as_float(v[4 * j + 3]) + b.w;
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r.x), "f"(r.y), "f"(r.z), "f"(r.w) : "memory");
+    for (int jj = 0; jj < 4; ++jj) {  // 8 columns: two 16-B fp32 chunks, one 16-B 16-bit chunk
+      float4 r[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = 2 * jj + h;
+        const int n = n0 + 4 * j;
+        const uint32_t a = buf + lane * 128 + ((j ^ (lane & 7)) << 4);
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(r[h].x), "=f"(r[h].y), "=f"(r[h].z), "=f"(r[h].w) : "r"(a) : "memory");
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias && n + 4 <= N) b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+        r[h].x += __uint_as_float(v[4 * j + 0]) + b.x;
+        r[h].y += __uint_as_float(v[4 * j + 1]) + b.y;
+        r[h].z += __uint_as_float(v[4 * j + 2]) + b.z;
+        r[h].w += __uint_as_float(v[4 * j + 3]) + b.w;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r[h].x), "f"(r[h].y), "f"(r[h].z), "f"(r[h].w) : "memory");
+      }
+      if (EMIT) {
+        st_s += (r[0].x + r[0].y) + (r[0].z + r[0].w) + (r[1].x + r[1].y) + (r[1].z + r[1].w);
+        st_q += (r[0].x * r[0].x + r[0].y * r[0].y) + (r[0].z * r[0].z + r[0].w * r[0].w) +
+                (r[1].x * r[1].x + r[1].y * r[1].y) + (r[1].z * r[1].z + r[1].w * r[1].w);
+        const uint32_t p0 = pack16x2(r[0].x, r[0].y, ep.fp16), p1 = pack16x2(r[0].z, r[0].w, ep.fp16);
+        const uint32_t p2 = pack16x2(r[1].x, r[1].y, ep.fp16), p3 = pack16x2(r[1].z, r[1].w, ep.fp16);
+        const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + jj);   // 16-B unit inside the 128-B box row
+        const uint32_t d16 = cx.stg16 + lane * 128 + ((unit ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d16), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+      }
+    }
+    if (EMIT && (c & 1)) {
+      // one 64-column slab of this row is complete
+      if (row0 + lane < M)
+        ep.stats_out[static_cast<long long>(row0 + lane) * (N >> 6) + ((n0 - 32) >> 6)] = make_float2(st_s, st_q);
+      st_s = 0.f;
+      st_q = 0.f;
     }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
       tma_store_2d(tmC, buf, n0, row0);
+      if (EMIT && (c & 1)) tma_store_2d(tmC16, cx.stg16, n0 - 32, row0);
       tma_store_commit();
     }
     if (STG_BUFS == 1 && c + 1 < CHUNKS) resid_issue_load<STG_BUFS>(tmR, N, row0, n0 + 32, cx, lane);
@@ -248,7 +288,7 @@ __device__ __forceinline__ void epilogue_generic(const GemmEpilogue& ep, int M, 
 // next_row0 < 0: no further tile for this CTA.
 template <int BLOCK_N, int MODE, int STG_BUFS, bool PAIR>
 __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, const CUtensorMap* tmC, const CUtensorMap* tmR,
-                                              int M, int N, int tile_row0, int tile_col0, int next_row0, int next_col0,
+                                              const CUtensorMap* tmC16, int M, int N, int tile_row0, int tile_col0, int next_row0, int next_col0,
                                               uint32_t tmem_acc, uint32_t tfull, uint32_t tfull_phase, uint32_t tempty,
                                               EpiCtx& cx, int warp, int lane) {
   constexpr int HALF_N = BLOCK_N / 2;
@@ -256,7 +296,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, const CUte
   const int row0 = tile_row0 + ew * 32;
   const int col0 = tile_col0 + half * HALF_N;
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(ew * 32) << 16) + half * HALF_N;
-  if (MODE == EPI_F32_RESID) {
+  if (MODE == EPI_F32_RESID || MODE == EPI_F32_RESID_EMIT) {
     // first residual box of this tile: requested before the accumulator is even ready
     if (row0 < M) resid_issue_load<STG_BUFS>(tmR, N, row0, col0, cx, lane);
     // and the residual boxes of the NEXT tile are pulled into L2 a whole main loop ahead
@@ -267,40 +307,62 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, const CUte
           if (nc + 32 * c < N) tma_prefetch_l2_2d(tmR, nc + 32 * c, nr);
     }
   }
+  // folded LayerNorm (EPI_16 modes): this thread's row statistics from the producer's per-slab partial sums, fetched
+  // while the main loop of this tile is still running
+  float ln_a = 1.f, ln_b = 0.f;
+  if ((MODE == EPI_16 || MODE == EPI_16_GELU) && ep.stats_in != nullptr && row0 + lane < M) {
+    const float2* sp = ep.stats_in + static_cast<long long>(row0 + lane) * ep.stats_parts;
+    float s = 0.f, q = 0.f;
+    for (int p = 0; p < ep.stats_parts; ++p) {
+      const float2 v = sp[p];
+      s += v.x;
+      q += v.y;
+    }
+    const float inv = 1.0f / static_cast<float>(ep.ln_width);
+    const float mean = s * inv;
+    const float var = fmaxf(q * inv - mean * mean, 0.f);
+    ln_a = rsqrtf(var + 1e-5f);
+    ln_b = -mean * ln_a;
+  }
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
   if (row0 >= M) {  // warp entirely below the matrix: nothing to store, just release the accumulator
     release_accumulator<PAIR>(tempty, lane);
     return;
   }
-  if (MODE == EPI_16) epilogue_16<HALF_N, false, STG_BUFS, PAIR>(ep, tmC, N, row0, col0, taddr, tempty, cx, lane);
-  else if (MODE == EPI_16_GELU) epilogue_16<HALF_N, true, STG_BUFS, PAIR>(ep, tmC, N, row0, col0, taddr, tempty, cx, lane);
-  else if (MODE == EPI_F32_RESID) epilogue_f32_resid<HALF_N, STG_BUFS, PAIR>(ep, tmC, tmR, N, row0, col0, taddr, tempty, cx, lane);
+  if (MODE == EPI_16) epilogue_16<HALF_N, false, STG_BUFS, PAIR>(ep, tmC, M, N, row0, col0, taddr, tempty, cx, lane, ln_a, ln_b);
+  else if (MODE == EPI_16_GELU) epilogue_16<HALF_N, true, STG_BUFS, PAIR>(ep, tmC, M, N, row0, col0, taddr, tempty, cx, lane, ln_a, ln_b);
+  else if (MODE == EPI_F32_RESID)
+    epilogue_f32_resid<HALF_N, STG_BUFS, PAIR, false>(ep, tmC, tmR, tmC16, M, N, row0, col0, taddr, tempty, cx, lane);
+  else if (MODE == EPI_F32_RESID_EMIT)
+    epilogue_f32_resid<HALF_N, STG_BUFS, PAIR, true>(ep, tmC, tmR, tmC16, M, N, row0, col0, taddr, tempty, cx, lane);
   else epilogue_generic<HALF_N, PAIR>(ep, M, N, row0, col0, taddr, tempty, cx.stg, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
 // 1-CTA kernel
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N>
+// EMIT (EPI_F32_RESID_EMIT) adds one 4-KB 16-bit staging box per epilogue warp and pays for it with one pipeline stage.
+template <int BLOCK_N, bool EMIT>
 struct GemmCfg {
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 5;
+  static constexpr int STAGES = ((BLOCK_N == 256) ? 4 : 5) - (EMIT ? 1 : 0);
   static constexpr int STG_BUFS = (BLOCK_N == 256) ? 1 : 2;
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (256 or 512)
   static constexpr uint32_t STG_BYTES = 8 * STG_BUFS * BOX_BYTES;
+  static constexpr uint32_t STG16_BYTES = EMIT ? 8 * BOX_BYTES : 0;
   static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 8 * 16 + 16;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;  // + align slack
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + STG16_BYTES + BAR_BYTES + 1024;  // + align slack
 };
 
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M, int N, int K,
-               GemmEpilogue ep) {
-  using Cfg = GemmCfg<BLOCK_N>;
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmC16, int M, int N, int K, GemmEpilogue ep) {
+  using Cfg = GemmCfg<BLOCK_N, MODE == EPI_F32_RESID_EMIT>;
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -308,7 +370,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
   const uint32_t stg_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = stg_base + Cfg::STG_BYTES;
+  const uint32_t stg16_base = stg_base + Cfg::STG_BYTES;
+  const uint32_t bar_base = stg16_base + Cfg::STG16_BYTES;
   auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
   auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + s); };
@@ -329,7 +392,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (MODE != EPI_GENERIC) tma_prefetch_desc(&tmC);
-    if (MODE == EPI_F32_RESID) tma_prefetch_desc(&tmR);
+    if (MODE == EPI_F32_RESID || MODE == EPI_F32_RESID_EMIT) tma_prefetch_desc(&tmR);
+    if (MODE == EPI_F32_RESID_EMIT) tma_prefetch_desc(&tmC16);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -403,7 +467,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
-    EpiCtx cx{stg_base + (warp - 4) * Cfg::STG_BUFS * BOX_BYTES, rbar_base + 16u * (warp - 4), 0u, 0u};
+    EpiCtx cx{stg16_base + (warp - 4) * BOX_BYTES, stg_base + (warp - 4) * Cfg::STG_BUFS * BOX_BYTES,
+              rbar_base + 16u * (warp - 4), 0u, 0u};
     uint32_t iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int te = ep.reverse ? total_tiles - 1 - tile : tile;
@@ -412,7 +477,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int nxe = ep.reverse ? total_tiles - 1 - nxt : nxt;
       const int nrow = nxt < total_tiles ? (nxe / n_tiles) * BLOCK_M : -1, ncol = nxt < total_tiles ? (nxe % n_tiles) * BLOCK_N : 0;
       const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
-      epilogue_tile<BLOCK_N, MODE, Cfg::STG_BUFS, false>(ep, &tmC, &tmR, M, N, m_blk * BLOCK_M, n_blk * BLOCK_N, nrow, ncol,
+      epilogue_tile<BLOCK_N, MODE, Cfg::STG_BUFS, false>(ep, &tmC, &tmR, &tmC16, M, N, m_blk * BLOCK_M, n_blk * BLOCK_N, nrow, ncol,
                                                           tmem_base + as * BLOCK_N, tfull_bar(as), aphase,
                                                           tempty_bar(as), cx, warp, lane);
     }
@@ -430,25 +495,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // CTA-pair kernel (cta_group::2), 256 x 256 tiles
 // ---------------------------------------------------------------------------------------------
+template <bool EMIT>
 struct PairCfg {
   static constexpr int BLOCK_N = 256;
-  static constexpr int STAGES = 5;
+  static constexpr int STAGES = EMIT ? 4 : 5;
   static constexpr int STG_BUFS = 2;
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;          // 128 x 64
   static constexpr uint32_t B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;    // this CTA's half: 128 x 64
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 512;
   static constexpr uint32_t STG_BYTES = 8 * STG_BUFS * BOX_BYTES;
+  static constexpr uint32_t STG16_BYTES = EMIT ? 8 * BOX_BYTES : 0;
   static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 8 * 16 + 16;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + STG16_BYTES + BAR_BYTES + 1024;
 };
 
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M, int N,
-                    int K, GemmEpilogue ep) {
-  using Cfg = PairCfg;
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                    const __grid_constant__ CUtensorMap tmC16, int M, int N, int K, GemmEpilogue ep) {
+  using Cfg = PairCfg<MODE == EPI_F32_RESID_EMIT>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BLOCK_N = Cfg::BLOCK_N;
 
@@ -457,7 +524,8 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
   const uint32_t stg_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = stg_base + Cfg::STG_BYTES;
+  const uint32_t stg16_base = stg_base + Cfg::STG_BYTES;
+  const uint32_t bar_base = stg16_base + Cfg::STG16_BYTES;
   auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };                       // used in the leader only
   auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };           // per CTA (multicast commit)
   auto tfull_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + s); };       // per CTA (multicast commit)
@@ -481,7 +549,8 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (MODE != EPI_GENERIC) tma_prefetch_desc(&tmC);
-    if (MODE == EPI_F32_RESID) tma_prefetch_desc(&tmR);
+    if (MODE == EPI_F32_RESID || MODE == EPI_F32_RESID_EMIT) tma_prefetch_desc(&tmR);
+    if (MODE == EPI_F32_RESID_EMIT) tma_prefetch_desc(&tmC16);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -557,7 +626,8 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
-    EpiCtx cx{stg_base + (warp - 4) * Cfg::STG_BUFS * BOX_BYTES, rbar_base + 16u * (warp - 4), 0u, 0u};
+    EpiCtx cx{stg16_base + (warp - 4) * BOX_BYTES, stg_base + (warp - 4) * Cfg::STG_BUFS * BOX_BYTES,
+              rbar_base + 16u * (warp - 4), 0u, 0u};
     uint32_t iter = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++iter) {
       const int te = ep.reverse ? total_tiles - 1 - tile : tile;
@@ -567,7 +637,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int nrow = nxt < total_tiles ? (nxe / n_tiles) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M : -1;
       const int ncol = nxt < total_tiles ? (nxe % n_tiles) * BLOCK_N : 0;
       const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
-      epilogue_tile<BLOCK_N, MODE, Cfg::STG_BUFS, true>(ep, &tmC, &tmR, M, N, m_pair * 2 * BLOCK_M + rank * BLOCK_M,
+      epilogue_tile<BLOCK_N, MODE, Cfg::STG_BUFS, true>(ep, &tmC, &tmR, &tmC16, M, N, m_pair * 2 * BLOCK_M + rank * BLOCK_M,
                                                          n_blk * BLOCK_N, nrow, ncol, tmem_base + as * BLOCK_N,
                                                          tfull_bar(as), aphase, tempty_bar(as), cx, warp, lane);
     }
@@ -586,7 +656,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // Host side
 // ---------------------------------------------------------------------------
 struct Maps {
-  CUtensorMap a, b, c, r;
+  CUtensorMap a, b, c, r, c16;
 };
 
 int build_maps(Maps& mp, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
@@ -597,14 +667,19 @@ int build_maps(Maps& mp, const void* A, long long lda, const void* B, long long 
   if (rc) return rc;
   mp.c = mp.a;
   mp.r = mp.a;  // placeholders for modes that do not use them
+  mp.c16 = mp.a;
   if (mode == EPI_16 || mode == EPI_16_GELU) {
     rc = make_tmap_2d(&mp.c, ep.out, 2, M, N, ep.ldo, 32, 64);
     if (rc) return rc;
-  } else if (mode == EPI_F32_RESID) {
+  } else if (mode == EPI_F32_RESID || mode == EPI_F32_RESID_EMIT) {
     rc = make_tmap_2d(&mp.c, ep.out, 4, M, N, ep.ldo, 32, 32);
     if (rc) return rc;
     rc = make_tmap_2d(&mp.r, ep.resid, 4, M, N, ep.ldr, 32, 32);
     if (rc) return rc;
+    if (mode == EPI_F32_RESID_EMIT) {
+      rc = make_tmap_2d(&mp.c16, ep.out16, 2, M, N, ep.ld16, 32, 64);
+      if (rc) return rc;
+    }
   }
   return 0;
 }
@@ -612,7 +687,7 @@ int build_maps(Maps& mp, const void* A, long long lda, const void* B, long long 
 template <int BLOCK_N, int MODE>
 int launch(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
            const GemmEpilogue& ep, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, MODE == EPI_F32_RESID_EMIT>;
   Maps mp;
   int rc = build_maps(mp, A, lda, B, ldb, M, N, K, ep, MODE, BLOCK_N);
   if (rc) return rc;
@@ -626,7 +701,7 @@ int launch(const void* A, long long lda, const void* B, long long ldb, int M, in
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, stream);  // work = algorithmic FLOPs
-  OVMR_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, mp.a, mp.b, mp.c, mp.r, M, N, K, ep));
+  OVMR_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, mp.a, mp.b, mp.c, mp.r, mp.c16, M, N, K, ep));
   count_launches(1);
   return 0;
 }
@@ -634,7 +709,7 @@ int launch(const void* A, long long lda, const void* B, long long ldb, int M, in
 template <int MODE>
 int launch_pair(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                 const GemmEpilogue& ep, cudaStream_t stream) {
-  using Cfg = PairCfg;
+  using Cfg = PairCfg<MODE == EPI_F32_RESID_EMIT>;
   Maps mp;
   int rc = build_maps(mp, A, lda, B, ldb, M, N, K, ep, MODE, Cfg::BLOCK_N / 2);
   if (rc) return rc;
@@ -649,8 +724,8 @@ int launch_pair(const void* A, long long lda, const void* B, long long ldb, int 
   const int max_clusters = num_sms() / 2;
   const int clusters = total < max_clusters ? total : max_clusters;
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, stream);
-  OVMR_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, mp.a, mp.b, mp.c, mp.r, M, N,
-                             K, ep));
+  OVMR_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, mp.a, mp.b, mp.c, mp.r, mp.c16, M,
+                             N, K, ep));
   count_launches(1);
   return 0;
 }
@@ -693,6 +768,8 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, i
   }
   OVMR_REQUIRE(bn == 128 || bn == 256 || bn == 512, "gemm: block_n must be 128, 256 or 512 (pair) (got %d)", bn);
   // ---- epilogue mode
+  OVMR_REQUIRE(ep.stats_in == nullptr || (ep.out_bf16 && ep.colsum != nullptr && ep.stats_parts > 0 && ep.ln_width > 0),
+               "gemm: folded LayerNorm needs a 16-bit output, colsum, stats_parts and ln_width");
   if (ep.out_bf16) {
     OVMR_REQUIRE(ep.ldo % 8 == 0, "gemm: 16-bit output needs ldo %% 8 == 0");
     return ep.act == 1 ? dispatch_tile<EPI_16_GELU>(bn, A, lda, B, ldb, M, N, K, ep, stream)
@@ -700,6 +777,13 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, i
   }
   const bool tma_resid = ep.resid != nullptr && ep.row_grp == 0 && ep.act == 0 && ep.alpha == 1.0f && ep.ldo % 4 == 0 &&
                          ep.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0;
+  if (ep.out16 != nullptr || ep.stats_out != nullptr) {
+    OVMR_REQUIRE(tma_resid && ep.out16 != nullptr && ep.stats_out != nullptr && N % 64 == 0 && ep.ld16 % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(ep.out16) & 15) == 0,
+                 "gemm: the 16-bit copy + row statistics need the fp32 residual epilogue, N %% 64 == 0 (N=%d) and an aligned out16",
+                 N);
+    return dispatch_tile<EPI_F32_RESID_EMIT>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+  }
   if (tma_resid) return dispatch_tile<EPI_F32_RESID>(bn, A, lda, B, ldb, M, N, K, ep, stream);
   return dispatch_tile<EPI_GENERIC>(bn, A, lda, B, ldb, M, N, K, ep, stream);
 }

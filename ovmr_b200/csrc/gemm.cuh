@@ -26,6 +26,20 @@ struct GemmEpilogue {
   float alpha = 1.0f;
   int row_grp = 0;
   int fp16 = 0;  // 16-bit format of A, B and of a 16-bit output: 0 = bf16, 1 = IEEE fp16
+  // ---- LayerNorm folding (api.cu: ln_1 / ln_2 never run as kernels inside a block) ----
+  // producer side (fp32-residual epilogue): additionally store a 16-bit copy of the new residual rows (the raw
+  // A operand of the next GEMM) and, per row and 64-column slab, the partial (sum, sum of squares) of the fp32
+  // values: stats_out[row * (N / 64) + slab].  Needs N % 64 == 0 and the TMA residual path.
+  void* out16 = nullptr;
+  long long ld16 = 0;
+  float2* stats_out = nullptr;
+  // consumer side (16-bit epilogue): out = act(rstd[m] * (acc - mean[m] * colsum[n]) + bias[n]) where acc was
+  // computed from the RAW rows and gamma-folded weights, colsum[n] = sum_k W'[n,k], bias[n] = b[n] + sum_k beta[k]
+  // W[n,k]; mean / rstd (eps 1e-5) come from stats_in[m * stats_parts + p] over rows of ln_width elements.
+  const float2* stats_in = nullptr;
+  int stats_parts = 0;
+  int ln_width = 0;
+  const float* colsum = nullptr;
   int reverse = 0;  // walk the output tiles last-to-first (see api.cu: alternating sweep direction keeps the
                     // rows the previous kernel wrote last — still resident in L2 — first in line)
 };

@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, long long ldx, int rows, const int* __restrict__ gather,
                  long long gather_mul, const float* __restrict__ w, const float* __restrict__ b,
                  float* out32, long long ld32, __nv_bfloat16* __restrict__ out16, long long ld16,
-                 const float* __restrict__ w2, const float* __restrict__ b2, int fp16, int reverse) {
+                 const float* __restrict__ w2, const float* __restrict__ b2, int fp16, int reverse,
+                 __nv_bfloat16* __restrict__ raw16, long long ld_raw, float2* __restrict__ stats, int parts) {
   constexpr int D = NV * 128;
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -58,11 +59,29 @@ layernorm_kernel(const float* x, long long ldx, int rows, const int* __restrict_
       v[i].w = (v[i].w - mean) * rstd * g4.w + b4.w;
     }
   };
-  normalise(w, b);
+  if (w) normalise(w, b);   // w == nullptr: identity (only the raw 16-bit copy + statistics are wanted)
   if (out32) {
     float4* o = reinterpret_cast<float4*>(out32 + static_cast<long long>(row) * ld32);
 #pragma unroll
     for (int i = 0; i < NV; ++i) o[lane + 32 * i] = v[i];
+  }
+  if (raw16) {
+    // LayerNorm folding (gemm.cuh): 16-bit copy of the fp32 row just written + its (sum, sum of squares) in the
+    // per-slab layout the GEMM epilogue reads (slab 0 carries the totals)
+    uint2* o = reinterpret_cast<uint2*>(raw16 + static_cast<long long>(row) * ld_raw);
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      uint2 p;
+      p.x = pack16x2(v[i].x, v[i].y, fp16);
+      p.y = pack16x2(v[i].z, v[i].w, fp16);
+      o[lane + 32 * i] = p;
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane < parts) stats[static_cast<long long>(row) * parts + lane] = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
   }
   if (w2) normalise(w2, b2);
   if (out16) {
@@ -338,10 +357,13 @@ inline int grid_for(long long work_items, int threads, int max_blocks_mult = 8) 
 
 int layernorm(const float* x, long long ldx, int rows, int D, const int* gather, long long gather_mul,
               const float* w, const float* b, float* out32, long long ld32, void* out16, long long ld16,
-              const float* w2, const float* b2, int fp16, cudaStream_t stream, int reverse) {
+              const float* w2, const float* b2, int fp16, cudaStream_t stream, int reverse, void* raw16, long long ld_raw,
+              float2* stats, int parts) {
   OVMR_REQUIRE(rows > 0, "layernorm: rows=%d", rows);
+  OVMR_REQUIRE(raw16 == nullptr || (stats != nullptr && parts > 0 && parts <= 32 && ld_raw % 4 == 0),
+               "layernorm: raw 16-bit copy needs a statistics buffer with 1..32 slabs");
   OVMR_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, "layernorm: D=%d must be a multiple of 128 in [128,1024]", D);
-  OVMR_REQUIRE(out32 || out16, "layernorm: no output");
+  OVMR_REQUIRE(out32 || out16 || raw16, "layernorm: no output");
   const int warps = 8;
   const int grid = (rows + warps - 1) / warps;
   auto* o16 = reinterpret_cast<__nv_bfloat16*>(out16);
@@ -350,7 +372,8 @@ int layernorm(const float* x, long long ldx, int rows, int D, const int* gather,
 #define LN_CASE(NV)                                                                                     \
   case NV:                                                                                              \
     OVMR_CHECK_CUDA(launch_pdl(layernorm_kernel<NV>, dim3(grid), dim3(warps * 32), 0, stream, x, ldx, rows, gather, \
-                               gather_mul, w, b, out32, ld32, o16, ld16, w2, b2, fp16, reverse));        \
+                               gather_mul, w, b, out32, ld32, o16, ld16, w2, b2, fp16, reverse,          \
+                               reinterpret_cast<__nv_bfloat16*>(raw16), ld_raw, stats, parts));                       \
     break;
   switch (D / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)

@@ -9,7 +9,8 @@ namespace ovmr {
 // <= 1 => identity). out32 (fp32) and/or out16 (bf16). If w2/b2 are given, out16 = LN2(LN(x)).
 int layernorm(const float* x, long long ldx, int rows, int D, const int* gather, long long gather_mul,
               const float* w, const float* b, float* out32, long long ld32, void* out16, long long ld16,
-              const float* w2, const float* b2, int fp16, cudaStream_t stream, int reverse = 0);
+              const float* w2, const float* b2, int fp16, cudaStream_t stream, int reverse = 0,
+              void* raw16 = nullptr, long long ld_raw = 0, float2* stats = nullptr, int parts = 0);
 
 int patchify(const float* images, void* out16, int B, int R, int P, int ldo, int fp16, cudaStream_t stream);
 // uint8 NCHW images with ToTensor + Normalize(mean_std[0..3), mean_std[3..6)) fused (host pointer to 6 floats)

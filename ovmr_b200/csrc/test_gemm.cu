@@ -36,6 +36,8 @@ struct Case {
   int out_bf16, act, bias, resid, row_grp, block_n;
   float alpha;
   int time_iters;
+  int emit = 0;  // fp32-residual epilogue + 16-bit copy + per-row slab statistics (LayerNorm folding, producer side)
+  int ln = 0;    // 16-bit epilogue with folded LayerNorm (consumer side)
 };
 
 static int run_case(const Case& c) {
@@ -87,6 +89,42 @@ static int run_case(const Case& c) {
   ep.act = c.act;
   ep.alpha = c.alpha;
   ep.row_grp = c.row_grp;
+  // ---- LayerNorm-folding operands
+  __nv_bfloat16* dout16 = nullptr;
+  float2* dstats = nullptr;
+  float* dcolsum = nullptr;
+  const int parts = N / 64;
+  std::vector<float> hmean, hrstd, hcolsum;
+  if (c.emit) {
+    CK(cudaMalloc(&dout16, (size_t)M * N * 2));
+    CK(cudaMemset(dout16, 0, (size_t)M * N * 2));
+    CK(cudaMalloc(&dstats, (size_t)M * parts * sizeof(float2)));
+    CK(cudaMemset(dstats, 0, (size_t)M * parts * sizeof(float2)));
+    ep.out16 = dout16;
+    ep.ld16 = N;
+    ep.stats_out = dstats;
+  }
+  const int ln_parts = 12, ln_width = 768;
+  if (c.ln) {
+    hmean.resize(M); hrstd.resize(M); hcolsum.resize(N);
+    std::vector<float2> hst((size_t)M * ln_parts);
+    for (int m = 0; m < M; ++m) {
+      const float mean = 0.3f * frand(), var = 0.5f + 0.4f * frand();
+      hmean[m] = mean;
+      hrstd[m] = 1.0f / sqrtf(var + 1e-5f);
+      for (int p = 0; p < ln_parts; ++p)
+        hst[(size_t)m * ln_parts + p] = make_float2(mean * ln_width / ln_parts, (var + mean * mean) * ln_width / ln_parts);
+    }
+    for (auto& v : hcolsum) v = frand();
+    CK(cudaMalloc(&dstats, hst.size() * sizeof(float2)));
+    CK(cudaMemcpy(dstats, hst.data(), hst.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&dcolsum, N * 4));
+    CK(cudaMemcpy(dcolsum, hcolsum.data(), N * 4, cudaMemcpyHostToDevice));
+    ep.stats_in = dstats;
+    ep.stats_parts = ln_parts;
+    ep.ln_width = ln_width;
+    ep.colsum = dcolsum;
+  }
   int rc = ovmr::gemm_tn(dA, K, dB, K, M, N, K, ep, 0, c.block_n);
   if (rc) {
     printf("[%s] launch failed rc=%d: %s\n", c.name, rc, ovmr::last_error());
@@ -117,6 +155,7 @@ static int run_case(const Case& c) {
       const float* b = &hB[(size_t)n * K];
       for (int k = 0; k < K; ++k) acc += (double)a[k] * (double)b[k];
       double v = c.alpha * acc + (c.bias ? hbias[n] : 0.0);
+      if (c.ln) v = hrstd[m] * (acc - hmean[m] * hcolsum[n]) + (c.bias ? hbias[n] : 0.0);
       if (c.act == 1) v = v / (1.0 + exp(-1.702 * v));
       if (c.resid) v += hres[(size_t)rrow * N + n];
       double got;
@@ -133,6 +172,29 @@ static int run_case(const Case& c) {
       if (err > max_err) max_err = err;
       if (fabs(v) > max_ref) max_ref = fabs(v);
     }
+  }
+  if (c.emit) {
+    // the 16-bit copy must be the rounding of the fp32 output, the slab statistics its sums (all rows)
+    std::vector<__nv_bfloat16> h16((size_t)M * N);
+    std::vector<float2> hst((size_t)M * parts);
+    CK(cudaMemcpy(h16.data(), dout16, h16.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hst.data(), dstats, hst.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+    const float* o = reinterpret_cast<float*>(hout.data());
+    long long bad16 = 0, badst = 0;
+    for (int m = 0; m < M; ++m) {
+      for (int p = 0; p < parts; ++p) {
+        double ss = 0, qq = 0;
+        for (int n = 64 * p; n < 64 * p + 64; ++n) {
+          const float x = o[(size_t)m * N + n];
+          ss += x; qq += (double)x * x;
+          if (__bfloat162float(h16[(size_t)m * N + n]) != bf16_round(x)) ++bad16;
+        }
+        const float2 g = hst[(size_t)m * parts + p];
+        if (fabs(g.x - ss) > 1e-3 * (1 + fabs(ss)) || fabs(g.y - qq) > 1e-3 * (1 + fabs(qq))) ++badst;
+      }
+    }
+    printf("    emit: 16-bit copy mismatches=%lld, slab-statistics mismatches=%lld\n", bad16, badst);
+    bad += bad16 + badst;
   }
   printf("[%s] M=%d N=%d K=%d bn=%d out=%s act=%d bias=%d resid=%d grp=%d : max_err=%.3e (max|ref|=%.3f) bad=%lld %s\n",
          c.name, M, N, K, c.block_n, c.out_bf16 ? "bf16" : "f32", c.act, c.bias, c.resid, c.row_grp, max_err,
@@ -155,6 +217,9 @@ static int run_case(const Case& c) {
   }
   fflush(stdout);
   cudaFree(dA); cudaFree(dB); cudaFree(dbias); cudaFree(dout);
+  if (dout16) cudaFree(dout16);
+  if (dstats) cudaFree(dstats);
+  if (dcolsum) cudaFree(dcolsum);
   if (c.resid && !inplace) cudaFree(dres);
   return bad ? 1 : 0;
 }
@@ -177,6 +242,11 @@ int main(int argc, char** argv) {
       {"ntail-alpha128", 256,  3000, 1536,  0,  0,  0,  0,  0, 128, 14.2857f, 0},
       {"multi-wave",    5000,  2304,  768,  1,  0,  1,  0,  0, 256, 1.0f, 0},
       {"heuristic",     1576,   512,  512,  1,  0,  1,  0,  0,   0, 1.0f, 0},
+      {"emit-128",       300,   768,  768,  0,  0,  1,  1,  0, 128, 1.0f, 0, 1, 0},
+      {"emit-256",      1000,   768, 3072,  0,  0,  1,  1,  0, 256, 1.0f, 0, 1, 0},
+      {"emit-pair",     1000,   768, 3072,  0,  0,  1,  1,  0, 512, 1.0f, 0, 1, 0},
+      {"ln-128",         300,  2304,  768,  1,  0,  1,  0,  0, 128, 1.0f, 0, 0, 1},
+      {"ln-gelu-pair",  1000,  3072,  768,  1,  1,  1,  0,  0, 512, 1.0f, 0, 0, 1},
   };
   if (!quick) {
     cases.push_back({"pair-small", 512, 512, 256, 0, 0, 1, 0, 0, 512, 1.0f, 0});
@@ -193,6 +263,10 @@ int main(int argc, char** argv) {
     cases.push_back({"vit-fc", 50432, 3072, 768, 1, 1, 1, 0, 0, 256, 1.0f, 10});
     cases.push_back({"vit-proj", 50432, 768, 3072, 0, 0, 1, 1, 0, 256, 1.0f, 10});
     cases.push_back({"vit-proj-128", 50432, 768, 3072, 0, 0, 1, 1, 0, 128, 1.0f, 10});
+    cases.push_back({"vit-out-pair-emit", 50432, 768, 768, 0, 0, 1, 1, 0, 512, 1.0f, 10, 1, 0});
+    cases.push_back({"vit-proj-pair-emit", 50432, 768, 3072, 0, 0, 1, 1, 0, 512, 1.0f, 10, 1, 0});
+    cases.push_back({"vit-qkv-pair-ln", 50432, 2304, 768, 1, 0, 1, 0, 0, 512, 1.0f, 10, 0, 1});
+    cases.push_back({"vit-fc-pair-ln", 50432, 3072, 768, 1, 1, 1, 0, 0, 512, 1.0f, 10, 0, 1});
   }
   int fails = 0;
   for (auto& c : cases) fails += run_case(c);

@@ -4,6 +4,7 @@ wrappers over the hot-path kernels.  PyTorch is used for device memory and strea
 """
 import ctypes as C
 import math
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -26,9 +27,13 @@ class PackedTransformer:
     """ovmr_transformer descriptor for a Transformer / TransformerDropout module
     (state_dict layout of clip/model.py:167-178)."""
 
-    def __init__(self, module, device, fp16: bool):
+    def __init__(self, module, device, fp16: bool, fold_ln: bool = False):
+        """fold_ln: also pack the LayerNorm-folded operands of QKV / c_fc (include/ovmr_b200.h): W' = W * gamma in the
+        tower's 16-bit format, colsum = row sums of the ROUNDED W' (what the tensor pipe actually multiplies by the
+        row mean), bias' = b + W . beta.  One-off host-side weight preparation."""
         blocks = list(module.resblocks)
         self.fp16 = bool(fp16)
+        self.fold_ln = bool(fold_ln)
         self.width = int(module.width)
         self.layers = len(blocks)
         self.heads = int(blocks[0].attn.num_heads)
@@ -43,6 +48,16 @@ class PackedTransformer:
                 "fc_w": _dev_16(b.mlp.c_fc.weight, device, fp16), "fc_b": _dev_f32(b.mlp.c_fc.bias, device),
                 "proj_w": _dev_16(b.mlp.c_proj.weight, device, fp16), "proj_b": _dev_f32(b.mlp.c_proj.bias, device),
             }
+            if self.fold_ln:
+                for name, lin_w, lin_b, ln in (("qkv", b.attn.in_proj_weight, b.attn.in_proj_bias, b.ln_1),
+                                               ("fc", b.mlp.c_fc.weight, b.mlp.c_fc.bias, b.ln_2)):
+                    w64 = lin_w.detach().to(device=device, dtype=torch.float64)
+                    gamma = ln.weight.detach().to(device=device, dtype=torch.float64)
+                    beta = ln.bias.detach().to(device=device, dtype=torch.float64)
+                    wf = _dev_16((w64 * gamma[None, :]).to(F32), device, fp16)
+                    fields[name + "_wf"] = wf
+                    fields[name + "_cs"] = wf.to(torch.float64).sum(dim=1).to(F32).contiguous()
+                    fields[name + "_bf"] = (lin_b.detach().to(device=device, dtype=torch.float64) + w64 @ beta).to(F32).contiguous()
             for k, v in fields.items():
                 setattr(arr[i], k, v.data_ptr())
                 self.keep.append(v)
@@ -92,7 +107,11 @@ class VisionEngine:
         self.k_pad = (k + 7) // 8 * 8
         conv = torch.zeros(D, self.k_pad, dtype=torch.float16 if fp16 else BF16, device=device)
         conv[:, :k] = _dev_16(w.reshape(D, k), device, fp16)
-        self.t = PackedTransformer(visual.transformer, device, fp16)
+        # LayerNorm folding inside the blocks of the image tower is implemented and parity-tested but OFF by default:
+        # measured on B200 (round 1) it trades 2 x 37 us of LayerNorm kernels per layer-batch for +47 us in the two
+        # residual GEMMs (extra 16-bit store, one pipeline stage less) and +100 us in the QKV / c_fc epilogues, a net
+        # loss (20.9k vs 22.9k img/s).  OVMR_FOLD_LN=1 enables it.
+        self.t = PackedTransformer(visual.transformer, device, fp16, fold_ln=os.environ.get("OVMR_FOLD_LN", "0") == "1")
         self.keep = dict(
             conv=conv, cls=_dev_f32(visual.class_embedding, device), pos=_dev_f32(visual.positional_embedding, device),
             ln_pre_w=_dev_f32(visual.ln_pre.weight, device), ln_pre_b=_dev_f32(visual.ln_pre.bias, device),

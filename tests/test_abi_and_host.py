@@ -24,14 +24,14 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ovmr_b200.h but not exported"
     assert sorted(L.SIGNATURES) == declared, "ctypes SIGNATURES out of sync with the header"
-    assert lib.ovmr_abi_version() == 1
+    assert lib.ovmr_abi_version() == 2
     assert isinstance(lib.ovmr_last_error(), bytes)
 
 
 def test_abi_struct_layout_matches_header():
     from ovmr_b200 import _lib as L
     p = ctypes.sizeof(ctypes.c_void_p)
-    assert ctypes.sizeof(L.BlockWeights) == 12 * p
+    assert ctypes.sizeof(L.BlockWeights) == 18 * p   # 12 operands + 6 LayerNorm-folded operands
     assert ctypes.sizeof(L.Transformer) == 4 * 4 + p
     assert L.Vit.transformer.offset == 5 * 4 + 4 + 8 * p  # 5 ints, padding, 8 pointers
     assert L.Text.transformer.offset == 3 * 4 + 4 + 4 * p

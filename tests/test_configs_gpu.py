@@ -166,3 +166,36 @@ def test_cfg2_encoder_is_batch_composition_invariant():
     assert torch.equal(a, b)
     # and a second run is bit-identical (no atomics / nondeterministic reductions on the path)
     assert torch.equal(eng.encode(img, normalize=True), a)
+
+
+# ------------------------------------------------------------------ LayerNorm folding on / off
+def test_layernorm_folding_matches_unfolded_tower(monkeypatch):
+    """The image tower with ln_1 / ln_2 folded into the QKV / c_fc GEMMs (raw 16-bit rows, gamma-folded weights,
+    row statistics from the residual epilogues) against the same tower with LayerNorm kernels and against the
+    fp32 oracle: ViT-B/16, non-trivial gamma / beta so that the folded operands are exercised."""
+    from ovmr_b200.clip.model import CLIP
+    from ovmr_b200.engine import VisionEngine
+    cfg = O.CLIP_CONFIGS["ViT-B/16"]
+    sd = O.init_clip_state(cfg, seed=0)
+    g = torch.Generator().manual_seed(77)
+    for k in list(sd):
+        if k.startswith("visual.transformer") and (".ln_1." in k or ".ln_2." in k):
+            noise = torch.randn(sd[k].shape, generator=g) * 0.2
+            sd[k] = (sd[k] + noise).bfloat16().float()
+    model = CLIP(*cfg)
+    model.load_state_dict(sd)
+    model = model.eval().to(DEV)
+    img = O.synth_images(40, 224, seed=5)          # 40 x 197 rows: the CTA-pair GEMM path
+    with torch.no_grad():
+        ref = O.l2n(O.encode_image(sd, img[:8]))
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("OVMR_FOLD_LN", flag)
+        eng = VisionEngine(model.visual, torch.device(DEV), fp16=False)
+        assert eng.t.fold_ln == (flag == "1")
+        outs[flag] = eng.encode(img.to(DEV), normalize=True).cpu()
+    assert _mincos(outs["1"], outs["0"]) > 0.99995
+    s = sd["logit_scale"].exp()
+    for flag in ("1", "0"):
+        assert _mincos(outs[flag][:8], ref) > 0.999, flag
+        assert (s * (outs[flag][:8] - ref)).abs().max() < 1e-2, flag

@@ -85,6 +85,27 @@ def test_encode_image_uint8_equals_float_path(tiny):
     assert torch.equal(a, b)
 
 
+def test_zeroshot_clip_baselines_match_oracle(tiny):
+    """trainers/zsclip.py: single-template ZeroshotCLIP and the 7(+1)-template ensemble ZeroshotCLIP2."""
+    from ovmr_b200.clip import tokenize
+    from ovmr_b200.trainers.zsclip import CUSTOM_TEMPLATES, IMAGENET_TEMPLATES_SELECT, ZeroshotCLIP, ZeroshotCLIP2
+    names = ["tabby_cat", "golden retriever", "fire truck", "espresso", "x"]
+    img = O.synth_images(6, tiny.res, seed=8)
+    for cls, ds in ((ZeroshotCLIP, "ImageNet"), (ZeroshotCLIP2, "ImageNet"), (ZeroshotCLIP2, "OxfordPets")):
+        zs = cls(tiny.clip, names, dataset_name=ds, device=DEV)
+        temps = [CUSTOM_TEMPLATES[ds]] if cls is ZeroshotCLIP else list(IMAGENET_TEMPLATES_SELECT) + (
+            [CUSTOM_TEMPLATES[ds]] if ds != "ImageNet" else [])
+        sets = [torch.cat([tokenize(t.format(n.replace("_", " "))) for n in names]) for t in temps]
+        ref_w = O.template_ensemble_classifier(tiny.sd, sets)
+        assert _mincos(zs.text_features, ref_w) > 0.999
+        ref_logits = O.zeroshot_logits(tiny.sd, img, ref_w)
+        out = zs.model_inference(img.to(DEV))
+        assert out.shape == ref_logits.shape
+        assert (out.cpu() - ref_logits).abs().max() < 2e-2
+        idx, val = zs.predict_topk(img.to(DEV), k=2)
+        assert idx.shape == (6, 2)
+
+
 def test_text_encoder_and_prompt_learner_api(tiny):
     """TextEncoder.forward(prompts, eos_index) and PromptLearner.forward's 5-tuple (reference call contract)."""
     pl_mod = tiny.model.prompt_learner

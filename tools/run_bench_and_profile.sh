@@ -1,13 +1,17 @@
-# Full bench (N=1) + ncu launch list + one full ncu capture of the top kernel. Run under gpurun.
+# ncu evidence for the N=1 bench command (run under gpurun, one GPU):
+#   1. launch list with per-launch duration and DRAM bytes (cold-cache, serialised: shares, not absolutes)
+#   2. one --set full capture of the dominant kernels of one transformer layer (source-level, for profiles/)
+# bench.py runs 3 warm-up steps + 1 timed + 1 event-profiled step; ~1060 launches per step at this size.
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err
-tail -c 3000 gpurun_out/bench_ours.json; tail -3 gpurun_out/bench_ours.err
-# launch list: small workload (same kernels, same shapes per batch), serialised cold-cache timings
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 400 --csv \
-    --log-file gpurun_out/launches.csv python bench.py --classes 32 --queries 1024 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launch_run.log 2>&1
-# full capture of the GEMM kernel (3 launches)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tn_kernel -s 200 -c 4 \
-    -o gpurun_out/prof_gemm -f python bench.py --classes 32 --queries 1024 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_run.log 2>&1
-ls -la gpurun_out | tail -12
+BENCH="python bench.py --classes 32 --queries 1024 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
+if [ "$1" != "full-only" ]; then
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+    -s 3200 -c 1100 --csv --log-file gpurun_out/launches_v2.csv $BENCH > gpurun_out/ncu_launch_run.log 2>&1
+tail -2 gpurun_out/ncu_launch_run.log
+fi
+# -s counts kernels matching -k: ~500 per step
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_tn_pair_kernel|attention_tc_kernel|layernorm_kernel" \
+    -s 1520 -c 8 -o gpurun_out/prof_layer_v2 -f $BENCH > gpurun_out/ncu_full_run.log 2>&1
+tail -2 gpurun_out/ncu_full_run.log
+ls -la gpurun_out | tail -5
