@@ -106,6 +106,15 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": sorted(reasons)}
 
 
+def measured_traffic():
+    """DRAM bytes per GEMM launch (mean over the GEMM class) from the committed ncu launch list of this command."""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("dram_bytes_per_launch"), f"ncu dram__bytes_read+write per launch, mean over {d.get('launches')} GEMM launches ({d.get('source')})"
+    return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -357,6 +366,7 @@ def main():
     if rank != 0:
         return
     peaks = measured_peaks()
+    traffic, traffic_src = measured_traffic()
     gemm = prof["gemm"]
     achieved = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
     kernel_ms = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items()}
@@ -377,7 +387,8 @@ def main():
         "clocks": clocks,
         "roofline": {"kernel": "gemm_tn_kernel (tcgen05/TMEM GEMM: QKV, out-proj, MLP, patch-embed, projections, logits)",
                      "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tflops"] if peaks["tflops"] else None, "traffic": None,
+                     "frac": achieved / peaks["tflops"] if peaks["tflops"] else None, "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "peak_source": peaks["source"], "launches_per_step": gemm["launches"] // max(1, args.steps),
                      "kernel_ms_per_step": kernel_ms, "ms_per_step_with_events": prof_ms_step,
                      "end_to_end_tensor_frac": ((C * S + Q) / world * GFLOP_PER_IMAGE / 1e3) / (ms_step / 1e3) / peaks["tflops"]},
