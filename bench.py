@@ -232,12 +232,35 @@ def main():
     q_dev = device_images(n_q_local, device, seed=1001 + rank)
     ex_labels = torch.arange(shard.lo, shard.hi, device=device).repeat_interleave(S)
 
+    def plan_batches(n, cap, unit=1):
+        """Split n items (each `unit` images) into batches of at most `cap` items.  Two candidates — full batches plus
+        a ragged tail, or ceil(n / cap) batches whose sizes differ by at most one — are compared with a wave model
+        of the persistent CTA-pair GEMMs (256 x 256 tiles over 74 SM pairs; QKV / out-proj / c_fc / c_proj of
+        ViT-B/16) and the cheaper one is used: a ragged tail costs whole waves, a slightly short batch may too."""
+        def cost(sizes):
+            c = 0
+            for z in sizes:
+                mp = -(-z * unit * 197 // 256)
+                c += sum(-(-mp * nt // 74) * k for nt, k in ((9, 1), (3, 1), (12, 1), (3, 4)))
+            return c
+        k = max(1, -(-n // cap))
+        base, extra = divmod(n, k)
+        even = [base + (1 if i < extra else 0) for i in range(k)]
+        ragged = [cap] * (n // cap) + ([n % cap] if n % cap else [])
+        sizes = even if cost(even) < cost(ragged) else ragged
+        offs = [0]
+        for z in sizes:
+            offs.append(offs[-1] + z)
+        return list(zip(offs[:-1], sizes))
+
+    ex_plan = [(o * S, z * S) for o, z in plan_batches(shard.size, cls_per_batch, unit=S)]   # whole classes per batch
+    q_plan = plan_batches(n_q_local, B)
+
     def exemplar_batches(images, labels):
-        step = cls_per_batch * S
-        return [{"img": images[i:i + step], "label": labels[i:i + step]} for i in range(0, images.shape[0], step)]
+        return [{"img": images[o:o + z], "label": labels[o:o + z]} for o, z in ex_plan]
 
     def query_batches(images):
-        return [images[i:i + B] for i in range(0, images.shape[0], B)]
+        return [images[o:o + z] for o, z in q_plan]
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
@@ -317,14 +340,12 @@ def main():
 
             def run_e2e(pool, what):
                 def host_ex_loader():
-                    step = cls_per_batch * S
-                    for bi, i in enumerate(range(0, n_ex_local, step)):
-                        n = min(step, n_ex_local - i)
-                        yield {"img": pool[bi % pool_n][:n], "label": ex_labels[i:i + n]}
+                    for bi, (o, z) in enumerate(ex_plan):
+                        yield {"img": pool[bi % pool_n][:z], "label": ex_labels[o:o + z]}
 
                 def host_q_loader():
-                    for bi, i in enumerate(range(0, n_q_local, B)):
-                        yield {"img": pool[bi % pool_n][:min(B, n_q_local - i)]}
+                    for bi, (o, z) in enumerate(q_plan):
+                        yield {"img": pool[bi % pool_n][:z]}
 
                 pf_e = DevicePrefetcher((), device)    # staging rings are allocated once and reused every step
                 pf_q = DevicePrefetcher((), device)

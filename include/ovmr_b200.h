@@ -156,6 +156,22 @@ int ovmr_patchify(const float* images, void* out_16bit, int batch, int resolutio
 int ovmr_patchify_u8(const uint8_t* images, const float* mean_std, void* out_16bit, int batch, int resolution, int patch,
                      int ldo, int fp16, void* stream);
 
+/* ---- input side: the reference's _transform (clip/clip.py:73-80) from decoded uint8 RGB pixels.
+ * Resize on a PIL image is Pillow's two-pass fixed-point resampler; ovmr_resample_coeffs restates its
+ * precompute_coeffs / normalize_coeffs_8bpc on the HOST in double precision (filter: 2 = bilinear, 3 = bicubic):
+ * bounds[2*i] = first source index, bounds[2*i+1] = window length, kk[i*ksize + k] = 22-bit fixed-point weights.
+ * Returns ksize (>0); with bounds == NULL or kk == NULL only the size is returned; -1 on error. */
+int ovmr_resample_coeffs(int in_size, int out_size, int filter, int* bounds, int* kk, int kk_capacity);
+/* Horizontal then vertical resampling pass (each rounding to uint8 as Pillow does) of one HWC uint8 RGB image
+ * [H, W, 3] to out_h x out_w with the centre crop folded in: only the crop window [crop_top, crop_top+crop_h) x
+ * [crop_left, crop_left+crop_w) is produced, as uint8 CHW [3, crop_h, crop_w] (input of ovmr_vit_forward_u8).
+ * xbounds / xk / ybounds / yk are DEVICE copies of the coefficient tables, ybounds_host the HOST copy (to size the
+ * intermediate); tmp needs rows_touched * crop_w * 3 bytes (<= H * crop_w * 3). */
+int ovmr_resize_crop_u8(const uint8_t* src_hwc, int H, int W, int out_h, int out_w, const int* xbounds, const int* xk,
+                        int xksize, const int* ybounds, const int* yk, int yksize, const int* ybounds_host, int crop_top,
+                        int crop_left, int crop_h, int crop_w, uint8_t* tmp, size_t tmp_bytes, uint8_t* dst_chw,
+                        void* stream);
+
 /* Text-tower input rows: out[(n*L+t),:] = src(n,t) + positional_embedding[t].
  *   mode 0: token_embedding[ids[n*ids_ld+t]]                       (clip/model.py:821-823)
  *   mode 1: prompts[n, t, :] of a [N, src_L, W] tensor              (trainers/...:81)

@@ -62,6 +62,10 @@ SIGNATURES = {
     "ovmr_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ovmr_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ovmr_patchify_u8": (c_int, [c_void_p, C.POINTER(c_float), c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ovmr_resample_coeffs": (c_int, [c_int, c_int, c_int, C.POINTER(c_int), C.POINTER(c_int), c_int]),
+    "ovmr_resize_crop_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                    c_int, C.POINTER(c_int), c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p,
+                                    c_void_p]),
     "ovmr_build_text_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_void_p]),
     "ovmr_agg_build": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -106,6 +106,32 @@ def test_zeroshot_clip_baselines_match_oracle(tiny):
         assert idx.shape == (6, 2)
 
 
+def test_classification_evaluator_matches_sklearn():
+    """dassl/evaluation/evaluator.py: accuracy / macro-F1 from device-side histograms == sklearn on the same lists,
+    for both input forms (the [B, C] output and the fused head's top-k indices)."""
+    from sklearn.metrics import f1_score
+    from ovmr_b200.evaluation import Classification
+    g = torch.Generator().manual_seed(3)
+    Cn, n = 23, 1000
+    y = torch.randint(0, Cn - 2, (n,), generator=g)            # two classes never occur as labels
+    logits = torch.randn(n, Cn, generator=g)
+    logits[torch.arange(n), y] += 1.5
+    ev = Classification(num_classes=Cn, device=DEV)
+    for i in range(0, n, 128):
+        ev.process(logits[i:i + 128].to(DEV), y[i:i + 128].to(DEV))
+    res = ev.evaluate()
+    pred = logits.argmax(1)
+    assert abs(res["accuracy"] - 100.0 * int((pred == y).sum()) / n) < 1e-9
+    ref = 100.0 * f1_score(y.numpy(), pred.numpy(), average="macro", labels=np.unique(y.numpy()))
+    assert abs(res["macro_f1"] - ref) < 1e-9
+    ev.reset()
+    top5 = logits.topk(5, dim=1)[1].to(torch.int32)
+    ev.process(top5.to(DEV), y.to(DEV), topk=5)
+    r5 = ev.evaluate()
+    assert abs(r5["accuracy"] - 100.0 * int((top5.long() == y[:, None]).any(1).sum()) / n) < 1e-9
+    assert abs(r5["macro_f1"] - ref) < 1e-9
+
+
 def test_text_encoder_and_prompt_learner_api(tiny):
     """TextEncoder.forward(prompts, eos_index) and PromptLearner.forward's 5-tuple (reference call contract)."""
     pl_mod = tiny.model.prompt_learner
