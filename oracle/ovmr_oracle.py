@@ -341,6 +341,33 @@ def zeroshot_logits(sd: State, images: Tensor, text_features: Tensor) -> Tensor:
     return sd["logit_scale"].exp() * f @ text_features.t()
 
 
+def coop_prompt_sets(sd: State, ctx: Tensor, tokenized_prompts: Tensor, template_tokens: Tensor, visual_tokens: Tensor):
+    """PromptLearner.forward of the CoOp-fusion variant (trainers/coop_mm_classifier.py:153-222), class token at the
+    end: ctx [n_ctx, W] (generic context), tokenized_prompts [C, 77] of "X .. X name.", template_tokens [1, 77] of
+    "X .. X.", visual_tokens [C, 2, W].  Returns [mm_prompts, v_prompts, t_prompts], each [C, 77, W]."""
+    n_ctx = ctx.shape[0]
+    emb = sd["token_embedding.weight"][tokenized_prompts]
+    tmpl = sd["token_embedding.weight"][template_tokens]
+    c = emb.shape[0]
+    prefix, suffix = emb[:, :1], emb[:, 1 + n_ctx:]
+    ctx_e = ctx.unsqueeze(0).expand(c, -1, -1)
+    mm = torch.cat([prefix, ctx_e, visual_tokens, suffix[:, :-2]], dim=1)
+    v = torch.cat([prefix, ctx_e, visual_tokens, tmpl[:, 1 + n_ctx:-2].repeat(c, 1, 1)], dim=1)
+    t = torch.cat([prefix, ctx_e, suffix], dim=1)
+    return [mm, v, t]
+
+
+def coop_text_features(sd: State, prompt_sets, tokenized_prompts: Tensor):
+    """TextEncoder.forward of the variant (:46-84): read-out at argmax + 2 for the mm / v sets, argmax for t;
+    L2-normalised."""
+    eot = tokenized_prompts.argmax(dim=-1)
+    out = []
+    for ind, p in enumerate(prompt_sets):
+        f = text_encoder(sd, p, eot + 2 if ind <= 1 else eot)
+        out.append(f / f.norm(dim=-1, keepdim=True))
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # Visual token generator + classifier generation
 # --------------------------------------------------------------------------------------

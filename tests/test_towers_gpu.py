@@ -132,6 +132,49 @@ def test_classification_evaluator_matches_sklearn():
     assert abs(r5["macro_f1"] - ref) < 1e-9
 
 
+def test_coop_fusion_variant_matches_oracle(tiny, tmp_path):
+    """trainers/coop_mm_classifier.py eval branch: prompt assembly from ctx + saved visual tokens, read-out rule
+    (argmax + 2 / argmax), F1 fusion weights (tau 10) and fused probabilities."""
+    from types import SimpleNamespace as NS
+    from ovmr_b200.clip import tokenize
+    from ovmr_b200.trainers import coop_mm_classifier as CM
+    n_cls, shots, n_ctx, W = 5, 3, 4, 128
+    g = torch.Generator().manual_seed(12)
+    vtok = torch.randn(n_cls, 2, W, generator=g) * 0.05
+    torch.save({"visual_tokens": vtok}, tmp_path / "visual_tokens.pt")
+    cfg = NS(TRAINER=NS(COOP=NS(N_CTX=n_ctx, CTX_INIT="", CSC=False, CLASS_TOKEN_POSITION="end",
+                                VISUAL_TOKEN_PATH=str(tmp_path / "visual_tokens.pt"))),
+             INPUT=NS(SIZE=(tiny.res, tiny.res)), DATALOADER=NS(TEST=NS(N_INS=shots)))
+    names = [f"class_{i}" for i in range(n_cls)]
+    torch.manual_seed(5)
+    model = CM.CustomCLIP(cfg, names, tiny.clip).eval()
+    ctx = model.prompt_learner.ctx.detach().cpu()
+    tok = tokenize(["X X X X " + n.replace("_", " ") + "." for n in names])
+    tmpl = tokenize("X X X X.")
+    sets = O.coop_prompt_sets(tiny.sd, ctx, tok, tmpl, vtok)
+    ours = model.prompt_learner()
+    for a, b in zip(ours, sets):
+        assert torch.equal(a.cpu(), b)
+    ref_cls = O.coop_text_features(tiny.sd, sets, tok)
+    our_cls = model.classifiers()
+    for a, b in zip(our_cls, ref_cls):
+        assert _mincos(a, b) > 0.999
+    ex = O.synth_images(n_cls * shots, tiny.res, seed=21)
+    labels = torch.arange(n_cls).repeat_interleave(shots)
+    qs = O.synth_images(7, tiny.res, seed=22)
+    loader = [{"img": ex.to(DEV), "label": labels.to(DEV)}]
+    probs = model(qs.to(DEV), eval_set_loader=loader)
+    feats = O.l2n(O.encode_image(tiny.sd, ex)).reshape(n_cls, shots, -1)
+    scale = tiny.sd["logit_scale"].exp()
+    fw, f1, preds = O.fusion_weights(scale, feats, ref_cls[0], ref_cls[1], ref_cls[2], 10.0)
+    if bool((model.exemplar_preds.cpu().long() == preds).all()):
+        assert (model.fusion_weight.cpu() - fw).abs().max() < 1e-6
+        ref_probs = O.classify(scale, O.l2n(O.encode_image(tiny.sd, qs)),
+                               {"mm_classifier": ref_cls[0], "vision_classifier": ref_cls[1],
+                                "text_classifier": ref_cls[2], "fusion_weight": fw}, "fusion")
+        assert (probs.cpu() - ref_probs).abs().max() < 2e-2
+
+
 def test_text_encoder_and_prompt_learner_api(tiny):
     """TextEncoder.forward(prompts, eos_index) and PromptLearner.forward's 5-tuple (reference call contract)."""
     pl_mod = tiny.model.prompt_learner
