@@ -144,6 +144,8 @@ class PromptLearner(nn.Module):
 class CustomCLIP(nn.Module):
     """trainers/...:179-364."""
 
+    GEN_GROUP = 128   # classes per aggregator / text-tower pass in forward_prompt
+
     def __init__(self, cfg, classnames, clip_model):
         super().__init__()
         self.cfg = cfg
@@ -217,6 +219,24 @@ class CustomCLIP(nn.Module):
         self.visual_tokens = torch.ones(n_cls, self.prompt_learner.n_ctx, e, dtype=f32, device=dev)
         self.eval_feat4cls = torch.zeros(n_cls, s, e, dtype=f32, device=dev)
         self.inference_text_initialized = torch.zeros(n_cls, dtype=torch.int32, device=dev)
+        # The per-class work behind the image encoder (aggregator + two text-tower passes over <= 16-token prompts)
+        # is launch-bound at the reference's batch of 16 classes: it is deferred and run once per GEN_GROUP classes
+        # (classes are independent, so the result is identical).
+        pending_feats, pending_labels, pending_n = [], [], 0
+
+        def flush():
+            nonlocal pending_feats, pending_labels, pending_n
+            if not pending_n:
+                return
+            feats = pending_feats[0] if len(pending_feats) == 1 else torch.cat(pending_feats)
+            labels = pending_labels[0] if len(pending_labels) == 1 else torch.cat(pending_labels)
+            mm, v, vtok = self._generate_batch(feats, labels)
+            self.mm_classifier[labels] = mm
+            self.visual_classifer[labels] = v
+            self.inference_text_initialized[labels] = 1
+            self.visual_tokens[labels] = vtok
+            pending_feats, pending_labels, pending_n = [], [], 0
+
         for batch_idx, batch in enumerate(eval_set_loader):
             image, label = batch["img"], batch["label"]
             if isinstance(image, list):  # K_TRANSFORMS views: interleave per sample (trainers/...:229-234)
@@ -228,11 +248,12 @@ class CustomCLIP(nn.Module):
             exemplar_label = label.reshape(num_cls, s)[:, 0]
             feats = self._vision().encode(image, normalize=True).view(num_cls, s, e)
             self.eval_feat4cls[exemplar_label] = feats
-            mm, v, vtok = self._generate_batch(feats, exemplar_label)
-            self.mm_classifier[exemplar_label] = mm
-            self.visual_classifer[exemplar_label] = v
-            self.inference_text_initialized[exemplar_label] = 1
-            self.visual_tokens[exemplar_label] = vtok
+            pending_feats.append(feats)
+            pending_labels.append(exemplar_label)
+            pending_n += num_cls
+            if pending_n >= self.GEN_GROUP:
+                flush()
+        flush()
         lo, hi = 0, n_cls
         if shard is not None and shard.world > 1:
             from .. import dist as D
