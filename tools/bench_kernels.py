@@ -4,8 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ovmr_b200 import _lib as L
 lib = L.lib()
 dev = "cuda"
-def timeit(fn, iters=20):
-    for _ in range(3): fn()
+def timeit(fn, iters=200):
+    for _ in range(20): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
