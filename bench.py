@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--classes", type=int, default=1000)
     ap.add_argument("--shots", type=int, default=16)
     ap.add_argument("--queries", type=int, default=50000)
-    ap.add_argument("--batch", type=int, default=256, help="images per encoder call (TEST.BATCH_SIZE of the reference)")
+    ap.add_argument("--batch", type=int, default=512, help="images per encoder call (TEST.BATCH_SIZE of the reference)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-classes", type=int, default=12,
@@ -223,6 +223,7 @@ def main():
     C, S, Q, B = args.classes, args.shots, args.queries, args.batch
     cls_per_batch = max(1, B // S)
     model = build_model(args, device)
+    model.image_encoder.engine(device).max_batch = max(B, 1)   # images per tower call = the bench batch
     shard = D.class_shard(C, rank, world)
     q_lo, q_hi = D.shard_range(Q, rank, world)
     n_ex_local, n_q_local = shard.size * S, q_hi - q_lo
@@ -402,7 +403,7 @@ def main():
                                 f"operands, text/aggregator towers {'fp16' if precision().text_fp16 else 'bf16'}, "
                                 f"fp32 accumulate/residual/statistics",
                    "l2_policy": f"inputs larger than L2: {(n_ex_local + n_q_local) * 602112 / 1e9:.1f} GB of images per "
-                                f"rank per step, ~0.9 GB of activations per batch (L2 = 126 MB)"},
+                                f"rank per step, ~{B * 3.6e-3:.1f} GB of activations per batch (L2 = 126 MB)"},
         "exemplar_img_s": C * S / (gen_ms / 1e3), "query_img_s": Q / (cls_ms / 1e3),
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -41,7 +41,8 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;         // 4 control warps + 8 epilogue warps
 constexpr uint32_t BOX_BYTES = 32 * 128;  // one epilogue staging box: 32 rows x 128 B
 
-enum EpiMode { EPI_GENERIC = 0, EPI_16 = 1, EPI_16_GELU = 2, EPI_F32_RESID = 3, EPI_F32_RESID_EMIT = 4 };
+enum EpiMode { EPI_GENERIC = 0, EPI_16 = 1, EPI_16_GELU = 2, EPI_F32_RESID = 3, EPI_F32_RESID_EMIT = 4,
+               EPI_16_LN = 5, EPI_16_GELU_LN = 6 };  // _LN: folded LayerNorm applied in the 16-bit epilogue
 
 __device__ __forceinline__ float quick_gelu(float x) {
   // x * sigmoid(1.702 x) with sigmoid(y) = 0.5 + 0.5 tanh(y/2): one MUFU op per element
@@ -74,11 +75,11 @@ __device__ __forceinline__ void release_accumulator(uint32_t tempty, int lane) {
 // ---------------------------------------------------------------------------------------------
 // EPI_16 / EPI_16_GELU: this warp's 32 rows x HALF_N columns, 64 columns (one 128-B box row) at a time.
 // ---------------------------------------------------------------------------------------------
-template <int HALF_N, bool GELU, int STG_BUFS, bool PAIR>
+template <int HALF_N, bool GELU, bool LN, int STG_BUFS, bool PAIR>
 __device__ __forceinline__ void epilogue_16(const GemmEpilogue& ep, const CUtensorMap* tmC, int M, int N, int row0, int col0,
                                             uint32_t taddr, uint32_t tempty, EpiCtx& cx, int lane, float ln_a, float ln_b) {
   constexpr int CHUNKS = HALF_N / 64;
-  const bool ln = ep.stats_in != nullptr;   // folded LayerNorm: out = ln_a * acc + ln_b * colsum[n] + bias[n]
+  constexpr bool ln = LN;   // folded LayerNorm: out = ln_a * acc + ln_b * colsum[n] + bias[n]
 #pragma unroll 1
   for (int c = 0; c < CHUNKS; ++c) {
     const int n0 = col0 + 64 * c;
@@ -205,7 +206,7 @@ __device__ __forceinline__ void epilogue_f32_resid(const GemmEpilogue& ep, const
     if (EMIT && (c & 1)) {
       // one 64-column slab of this row is complete
       if (row0 + lane < M)
-        ep.stats_out[static_cast<long long>(row0 + lane) * (N >> 6) + ((n0 - 32) >> 6)] = make_float2(st_s, st_q);
+        ep.stats_out[static_cast<long long>((n0 - 32) >> 6) * M + (row0 + lane)] = make_float2(st_s, st_q);   // [slab][M]
       st_s = 0.f;
       st_q = 0.f;
     }
@@ -310,13 +311,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, const CUte
   // folded LayerNorm (EPI_16 modes): this thread's row statistics from the producer's per-slab partial sums, fetched
   // while the main loop of this tile is still running
   float ln_a = 1.f, ln_b = 0.f;
-  if ((MODE == EPI_16 || MODE == EPI_16_GELU) && ep.stats_in != nullptr && row0 + lane < M) {
-    const float2* sp = ep.stats_in + static_cast<long long>(row0 + lane) * ep.stats_parts;
+  if ((MODE == EPI_16_LN || MODE == EPI_16_GELU_LN) && row0 + lane < M) {
+    // slab-major layout [slab][M]: the 32 rows of this warp read 256 contiguous bytes per slab (coalesced), all
+    // slabs in flight at once; <= 16 slabs (D <= 1024)
+    const float2* sp = ep.stats_in + (row0 + lane);
+    float2 pv[16];
+#pragma unroll
+    for (int p = 0; p < 16; ++p)
+      pv[p] = p < ep.stats_parts ? __ldcg(sp + static_cast<long long>(p) * M) : make_float2(0.f, 0.f);
     float s = 0.f, q = 0.f;
-    for (int p = 0; p < ep.stats_parts; ++p) {
-      const float2 v = sp[p];
-      s += v.x;
-      q += v.y;
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+      s += pv[p].x;
+      q += pv[p].y;
     }
     const float inv = 1.0f / static_cast<float>(ep.ln_width);
     const float mean = s * inv;
@@ -330,8 +337,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, const CUte
     release_accumulator<PAIR>(tempty, lane);
     return;
   }
-  if (MODE == EPI_16) epilogue_16<HALF_N, false, STG_BUFS, PAIR>(ep, tmC, M, N, row0, col0, taddr, tempty, cx, lane, ln_a, ln_b);
-  else if (MODE == EPI_16_GELU) epilogue_16<HALF_N, true, STG_BUFS, PAIR>(ep, tmC, M, N, row0, col0, taddr, tempty, cx, lane, ln_a, ln_b);
+  if (MODE == EPI_16) epilogue_16<HALF_N, false, false, STG_BUFS, PAIR>(ep, tmC, M, N, row0, col0, taddr, tempty, cx, lane, ln_a, ln_b);
+  else if (MODE == EPI_16_GELU) epilogue_16<HALF_N, true, false, STG_BUFS, PAIR>(ep, tmC, M, N, row0, col0, taddr, tempty, cx, lane, ln_a, ln_b);
+  else if (MODE == EPI_16_LN) epilogue_16<HALF_N, false, true, STG_BUFS, PAIR>(ep, tmC, M, N, row0, col0, taddr, tempty, cx, lane, ln_a, ln_b);
+  else if (MODE == EPI_16_GELU_LN) epilogue_16<HALF_N, true, true, STG_BUFS, PAIR>(ep, tmC, M, N, row0, col0, taddr, tempty, cx, lane, ln_a, ln_b);
   else if (MODE == EPI_F32_RESID)
     epilogue_f32_resid<HALF_N, STG_BUFS, PAIR, false>(ep, tmC, tmR, tmC16, M, N, row0, col0, taddr, tempty, cx, lane);
   else if (MODE == EPI_F32_RESID_EMIT)
@@ -668,7 +677,7 @@ int build_maps(Maps& mp, const void* A, long long lda, const void* B, long long 
   mp.c = mp.a;
   mp.r = mp.a;  // placeholders for modes that do not use them
   mp.c16 = mp.a;
-  if (mode == EPI_16 || mode == EPI_16_GELU) {
+  if (mode == EPI_16 || mode == EPI_16_GELU || mode == EPI_16_LN || mode == EPI_16_GELU_LN) {
     rc = make_tmap_2d(&mp.c, ep.out, 2, M, N, ep.ldo, 32, 64);
     if (rc) return rc;
   } else if (mode == EPI_F32_RESID || mode == EPI_F32_RESID_EMIT) {
@@ -772,6 +781,11 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, i
                "gemm: folded LayerNorm needs a 16-bit output, colsum, stats_parts and ln_width");
   if (ep.out_bf16) {
     OVMR_REQUIRE(ep.ldo % 8 == 0, "gemm: 16-bit output needs ldo %% 8 == 0");
+    if (ep.stats_in != nullptr) {
+      OVMR_REQUIRE(ep.stats_parts <= 16, "gemm: folded LayerNorm supports at most 16 slabs (width <= 1024)");
+      return ep.act == 1 ? dispatch_tile<EPI_16_GELU_LN>(bn, A, lda, B, ldb, M, N, K, ep, stream)
+                         : dispatch_tile<EPI_16_LN>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+    }
     return ep.act == 1 ? dispatch_tile<EPI_16_GELU>(bn, A, lda, B, ldb, M, N, K, ep, stream)
                        : dispatch_tile<EPI_16>(bn, A, lda, B, ldb, M, N, K, ep, stream);
   }

@@ -29,13 +29,14 @@ struct GemmEpilogue {
   // ---- LayerNorm folding (api.cu: ln_1 / ln_2 never run as kernels inside a block) ----
   // producer side (fp32-residual epilogue): additionally store a 16-bit copy of the new residual rows (the raw
   // A operand of the next GEMM) and, per row and 64-column slab, the partial (sum, sum of squares) of the fp32
-  // values: stats_out[row * (N / 64) + slab].  Needs N % 64 == 0 and the TMA residual path.
+  // values, slab-major: stats_out[slab * M + row] (coalesced for both sides).  Needs N % 64 == 0 and the TMA
+  // residual path.
   void* out16 = nullptr;
   long long ld16 = 0;
   float2* stats_out = nullptr;
   // consumer side (16-bit epilogue): out = act(rstd[m] * (acc - mean[m] * colsum[n]) + bias[n]) where acc was
   // computed from the RAW rows and gamma-folded weights, colsum[n] = sum_k W'[n,k], bias[n] = b[n] + sum_k beta[k]
-  // W[n,k]; mean / rstd (eps 1e-5) come from stats_in[m * stats_parts + p] over rows of ln_width elements.
+  // W[n,k]; mean / rstd (eps 1e-5) come from stats_in[p * M + m], p < stats_parts, over rows of ln_width elements.
   const float2* stats_in = nullptr;
   int stats_parts = 0;
   int ln_width = 0;

@@ -67,7 +67,7 @@ layernorm_kernel(const float* x, long long ldx, int rows, const int* __restrict_
   }
   if (raw16) {
     // LayerNorm folding (gemm.cuh): 16-bit copy of the fp32 row just written + its (sum, sum of squares) in the
-    // per-slab layout the GEMM epilogue reads (slab 0 carries the totals)
+    // slab-major layout the GEMM epilogue reads (slab 0 carries the totals)
     uint2* o = reinterpret_cast<uint2*>(raw16 + static_cast<long long>(row) * ld_raw);
     float s = 0.f, q = 0.f;
 #pragma unroll
@@ -81,7 +81,8 @@ layernorm_kernel(const float* x, long long ldx, int rows, const int* __restrict_
     }
     s = warp_sum(s);
     q = warp_sum(q);
-    if (lane < parts) stats[static_cast<long long>(row) * parts + lane] = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
+    if (lane < parts)   // slab-major [slab][rows]
+      stats[static_cast<long long>(lane) * rows + row] = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
   }
   if (w2) normalise(w2, b2);
   if (out16) {

@@ -113,7 +113,7 @@ static int run_case(const Case& c) {
       hmean[m] = mean;
       hrstd[m] = 1.0f / sqrtf(var + 1e-5f);
       for (int p = 0; p < ln_parts; ++p)
-        hst[(size_t)m * ln_parts + p] = make_float2(mean * ln_width / ln_parts, (var + mean * mean) * ln_width / ln_parts);
+        hst[(size_t)p * M + m] = make_float2(mean * ln_width / ln_parts, (var + mean * mean) * ln_width / ln_parts);
     }
     for (auto& v : hcolsum) v = frand();
     CK(cudaMalloc(&dstats, hst.size() * sizeof(float2)));
@@ -189,7 +189,7 @@ static int run_case(const Case& c) {
           ss += x; qq += (double)x * x;
           if (__bfloat162float(h16[(size_t)m * N + n]) != bf16_round(x)) ++bad16;
         }
-        const float2 g = hst[(size_t)m * parts + p];
+        const float2 g = hst[(size_t)p * M + m];
         if (fabs(g.x - ss) > 1e-3 * (1 + fabs(ss)) || fabs(g.y - qq) > 1e-3 * (1 + fabs(qq))) ++badst;
       }
     }
@@ -263,6 +263,9 @@ int main(int argc, char** argv) {
     cases.push_back({"vit-fc", 50432, 3072, 768, 1, 1, 1, 0, 0, 256, 1.0f, 10});
     cases.push_back({"vit-proj", 50432, 768, 3072, 0, 0, 1, 1, 0, 256, 1.0f, 10});
     cases.push_back({"vit-proj-128", 50432, 768, 3072, 0, 0, 1, 1, 0, 128, 1.0f, 10});
+    cases.push_back({"vit-qkv-pair-nobias", 50432, 2304, 768, 1, 0, 0, 0, 0, 512, 1.0f, 10});
+    cases.push_back({"vit-fc-pair-nobias", 50432, 3072, 768, 1, 1, 0, 0, 0, 512, 1.0f, 10});
+    cases.push_back({"vit-fc-pair-nogelu", 50432, 3072, 768, 1, 0, 1, 0, 0, 512, 1.0f, 10});
     cases.push_back({"vit-out-pair-emit", 50432, 768, 768, 0, 0, 1, 1, 0, 512, 1.0f, 10, 1, 0});
     cases.push_back({"vit-proj-pair-emit", 50432, 768, 3072, 0, 0, 1, 1, 0, 512, 1.0f, 10, 1, 0});
     cases.push_back({"vit-qkv-pair-ln", 50432, 2304, 768, 1, 0, 1, 0, 0, 512, 1.0f, 10, 0, 1});

@@ -95,7 +95,7 @@ def transformer_forward(pt: PackedTransformer, x: torch.Tensor, n_seq: int, seq_
 class VisionEngine:
     """VisionTransformer.forward (clip/model.py:411-428) through ovmr_vit_forward."""
 
-    def __init__(self, visual, device, fp16: bool, max_batch: int = 256):
+    def __init__(self, visual, device, fp16: bool, max_batch: int = 512):
         self.device = device
         self.fp16 = bool(fp16)
         self.max_batch = max_batch
@@ -108,9 +108,10 @@ class VisionEngine:
         conv = torch.zeros(D, self.k_pad, dtype=torch.float16 if fp16 else BF16, device=device)
         conv[:, :k] = _dev_16(w.reshape(D, k), device, fp16)
         # LayerNorm folding inside the blocks of the image tower is implemented and parity-tested but OFF by default:
-        # measured on B200 (round 1) it trades 2 x 37 us of LayerNorm kernels per layer-batch for +47 us in the two
-        # residual GEMMs (extra 16-bit store, one pipeline stage less) and +100 us in the QKV / c_fc epilogues, a net
-        # loss (20.9k vs 22.9k img/s).  OVMR_FOLD_LN=1 enables it.
+        # measured on B200 (round 1, 256-image batch) it trades 2 x 37 us of LayerNorm kernels per layer for +41 us in
+        # the two residual GEMMs (extra 16-bit store, one pipeline stage less) and +43 us in the QKV / c_fc
+        # epilogues (after making the row statistics slab-major / coalesced and the LN epilogue a compile-time
+        # variant; +100 us before) — still a small net loss.  OVMR_FOLD_LN=1 enables it.
         self.t = PackedTransformer(visual.transformer, device, fp16, fold_ln=os.environ.get("OVMR_FOLD_LN", "0") == "1")
         self.keep = dict(
             conv=conv, cls=_dev_f32(visual.class_embedding, device), pos=_dev_f32(visual.positional_embedding, device),
