@@ -35,7 +35,7 @@ __device__ __forceinline__ float ex2f(float x) {
 template <bool FP16>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                    void* __restrict__ out_, int n_seq, int L, int Lpad, int D, int heads, int causal,
+                    const __grid_constant__ CUtensorMap tmO, void* __restrict__ out_, int n_seq, int L, int Lpad, int D, int heads, int causal,
                     float scale_log2e, int reverse) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -58,6 +58,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   auto r_free = [&](uint32_t s) { return bars + 8u * (14 + s); };
   const uint32_t tmem_slot = bars + 8u * 16;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+  // output staging: one 32-row x 128-B swizzled box per softmax warp (TMA store), 1024-B aligned
+  const uint32_t sO = (tmem_slot + 16u + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_work = n_seq * heads;
@@ -66,6 +68,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (uint32_t s = 0; s < 2; ++s) {
@@ -291,7 +294,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(o_full(r), n & 1u);
         tc_fence_after();
         const float inv = 1.0f / sum;
-        uint16_t* orow = reinterpret_cast<uint16_t*>(out_) + (static_cast<long long>(seq) * L + q_idx) * D + h * 64;
+        // Each thread's 128-B output row goes into this warp's swizzled staging box and ONE lane issues a TMA store
+        // of the 32-row box (clipped at the sequence's last row by the 3-D tensor map).  Row-strided 16-byte global
+        // stores from 32 lanes cost ~250 cycles per instruction here (8 per thread: two thirds of the output step).
+        const uint32_t stg = sO + (warp - 4) * 4096u;
+        if (lane == 0) tma_store_wait_read<0>();   // the previous store of this warp has read the box
+        __syncwarp();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t v[16];
@@ -301,20 +309,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tc_fence_before();
             mbar_arrive(r_free(r));   // region reusable: everything of this tile is in registers
           }
-          if (q_idx < L) {
-            uint4 o0, o1;
-            auto pk2 = [&](int e) {
-              const float a = __uint_as_float(v[e]) * inv, b = __uint_as_float(v[e + 1]) * inv;
-              return FP16 ? pack_f16x2(a, b) : pack_bf16x2(a, b);
-            };
-            o0.x = pk2(0); o0.y = pk2(2); o0.z = pk2(4); o0.w = pk2(6);
-            o1.x = pk2(8); o1.y = pk2(10); o1.z = pk2(12); o1.w = pk2(14);
-            reinterpret_cast<uint4*>(orow + 16 * c)[0] = o0;
-            reinterpret_cast<uint4*>(orow + 16 * c)[1] = o1;
+          auto pk2 = [&](int e) {
+            const float a = __uint_as_float(v[e]) * inv, b = __uint_as_float(v[e + 1]) * inv;
+            return FP16 ? pack_f16x2(a, b) : pack_bf16x2(a, b);
+          };
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {   // two 16-byte units of the 128-byte row
+            const uint32_t dst = stg + lane * 128u + (((2u * c + u) ^ (lane & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk2(8 * u)), "r"(pk2(8 * u + 2)),
+                         "r"(pk2(8 * u + 4)), "r"(pk2(8 * u + 6))
+                         : "memory");
           }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        const int row0 = j * QTILE + static_cast<int>(quarter) * 32;
+        if (lane == 0 && row0 < L) {
+          tma_store_3d(&tmO, stg, h * 64, row0, seq);
+          tma_store_commit();
         }
       }
     }
+    if (lane == 0) tma_store_wait<0>();   // all output boxes written before the CTA retires
   }
 
   tc_fence_before();
@@ -337,11 +353,14 @@ int attention_tc(const void* qkv, void* out, int n_seq, int L, int D, int heads,
   if (rc) return rc;
   rc = make_tmap_16b(&tmKV, qkv, rows, 3LL * D, 3LL * D, Lpad);
   if (rc) return rc;
+  CUtensorMap tmO;
+  rc = make_tmap_3d_16b(&tmO, out, D, L, n_seq, D, static_cast<long long>(L) * D, 32);
+  if (rc) return rc;
   const uint32_t kv_stride = (static_cast<uint32_t>(Lpad) * 128u + 1023u) & ~1023u;
-  const size_t smem = 2 * Q_BYTES + 4 * static_cast<size_t>(kv_stride) + 8 * 17 + 16 + 1024;
+  const size_t smem = 2 * Q_BYTES + 4 * static_cast<size_t>(kv_stride) + 8 * 17 + 16 + 1024 + 8 * 4096 + 1024;  // + output boxes
   static bool configured = false;
   if (!configured) {
-    const int max_smem = 2 * Q_BYTES + 4 * 32768 + 8 * 17 + 16 + 1024;
+    const int max_smem = 2 * Q_BYTES + 4 * 32768 + 8 * 17 + 16 + 1024 + 8 * 4096 + 1024;
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
@@ -351,10 +370,10 @@ int attention_tc(const void* qkv, void* out, int n_seq, int L, int D, int heads,
   const float scale_log2e = 0.125f * 1.4426950408889634f;
   ProfScope prof(PROF_ATTENTION, 4.0 * n_seq * heads * static_cast<double>(L) * L * 64 * (causal ? 0.5 : 1.0), stream);
   if (fp16)
-    OVMR_CHECK_CUDA(launch_pdl(attention_tc_kernel<true>, dim3(grid), dim3(ATC_THREADS), smem, stream, tmQ, tmKV, out, n_seq, L,
+    OVMR_CHECK_CUDA(launch_pdl(attention_tc_kernel<true>, dim3(grid), dim3(ATC_THREADS), smem, stream, tmQ, tmKV, tmO, out, n_seq, L,
                                Lpad, D, heads, causal, scale_log2e, reverse));
   else
-    OVMR_CHECK_CUDA(launch_pdl(attention_tc_kernel<false>, dim3(grid), dim3(ATC_THREADS), smem, stream, tmQ, tmKV, out, n_seq, L,
+    OVMR_CHECK_CUDA(launch_pdl(attention_tc_kernel<false>, dim3(grid), dim3(ATC_THREADS), smem, stream, tmQ, tmKV, tmO, out, n_seq, L,
                                Lpad, D, heads, causal, scale_log2e, reverse));
   count_launches(1);
   return 0;

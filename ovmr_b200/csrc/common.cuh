@@ -23,6 +23,10 @@ int num_sms();
 void count_launches(int n);  // bookkeeping for ovmr_launch_count()
 // TMA descriptor of a 16-bit row-major matrix, boxes of box_rows x 64 elements, 128-byte swizzle (zero OOB fill)
 int make_tmap_16b(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
+// 16-bit tensor [d2][d1][d0] (d0 contiguous; strides in elements), boxes of 1 x box_rows x 64, 128-byte swizzle:
+// stores are clipped at d1 (a sequence's last row), not only at the end of the allocation
+int make_tmap_3d_16b(CUtensorMap* map, const void* base, long long d0, long long d1, long long d2, long long stride1,
+                     long long stride2, int box_rows);
 // general form: element size 2 or 4 bytes, box inner extent must be 128 bytes
 int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, long long rows, long long cols, long long ld,
                  int box_rows, int box_cols);
@@ -224,6 +228,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem
                                              int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1,
+                                             int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() {

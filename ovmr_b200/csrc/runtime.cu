@@ -139,6 +139,27 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, long long r
   return 0;
 }
 
+int make_tmap_3d_16b(CUtensorMap* map, const void* base, long long d0, long long d1, long long d2, long long stride1,
+                     long long stride2, int box_rows) {
+  auto enc = tensor_map_encoder();
+  if (!enc) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    return OVMR_ERR_INVALID;
+  }
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(stride1) * 2, static_cast<cuuint64_t>(stride2) * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (3d) failed (%d) base=%p dims=%lld x %lld x %lld", (int)r, base, d0, d1, d2);
+    return OVMR_ERR_INVALID;
+  }
+  return 0;
+}
+
 int make_tmap_16b(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
   return make_tmap_2d(map, base, 2, rows, cols, ld, box_rows, 64);
 }

@@ -17,12 +17,7 @@ cdll.ovmr_debug_attn_trace(buf, n)
 L.check(lib.ovmr_attention(qkv.data_ptr(), out.data_ptr(), B, Lq, D, H, 0, 0, L.stream()))
 torch.cuda.synchronize()
 cdll.ovmr_debug_attn_trace(buf, n)
-names = ["S_issue", "PV_issue", "iter_start", "s_full", "pass1_done", "exp1_done", "o_full", "out_done", "exp2_done", "arrived", "S_begin", "PV_begin", "r_free_ok", "q_full_ok", "Q_load"]
-t0 = buf[2 * 40 + 4]
-for t in range(4, 10):
-    print(t, "r_free arrive per warp:", [buf[(12 + w) * 40 + t] - t0 for w in range(4, 12)])
-for t in range(4, 8):
-    for off, nm in ((0, "warp4"), (40, "warp8")):
-        print(t, nm, " ".join(f"{names[s]}={buf[(s+off)*40+t]-t0}" for s in range(2, 10)))
-for t in range(4, 4):
-    print(t, " ".join(f"{names[s]}={buf[s*40+t]-t0}" for s in range(15)))
+names = ["o_full", "ld0", "ld1", "ld2", "ld3", "stored", "iter_start"]
+for t in range(8, 20, 2):
+    t0 = buf[0 * 40 + t]
+    print(t, " ".join(f"{names[s]}={buf[s*40+t]-t0}" for s in range(7)), "next_iter_start=", buf[6*40+t+2]-t0)
