@@ -272,7 +272,11 @@ int main(int argc, char** argv) {
     cases.push_back({"vit-fc-pair-ln", 50432, 3072, 768, 1, 1, 1, 0, 0, 512, 1.0f, 10, 0, 1});
   }
   int fails = 0;
-  for (auto& c : cases) fails += run_case(c);
+  const char* only = (argc > 2 && !strcmp(argv[1], "only")) ? argv[2] : nullptr;   // build/test_gemm only <case-name>
+  for (auto& c : cases) {
+    if (only && strcmp(only, c.name)) continue;
+    fails += run_case(c);
+  }
   printf("test_gemm: %d/%zu cases failed\n", fails, cases.size());
   return fails ? 1 : 0;
 }
