@@ -415,6 +415,19 @@ def main():
                      "kernel_ms_per_step": kernel_ms, "ms_per_step_with_events": prof_ms_step,
                      "end_to_end_tensor_frac": ((C * S + Q) / world * GFLOP_PER_IMAGE / 1e3) / (ms_step / 1e3) / peaks["tflops"]},
     }
+    # the other kernel classes against their own rooflines (same event-timed pass): HBM-bound classes in GB/s of
+    # algorithmic bytes against the measured copy bandwidth, attention in TFLOP/s of algorithmic FLOPs
+    def _cls(name, bound, unit_scale, peak):
+        c = prof[name]
+        ach = c["work"] / (c["ms"] * 1e-3) / unit_scale if c["ms"] > 0 else 0.0
+        return {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                "frac": ach / peak if peak else None, "launches_per_step": c["launches"] // max(1, args.steps)}
+    line["roofline"]["other_classes"] = [
+        _cls("layernorm", "hbm", 1e9, peaks["hbm_gbs"]),
+        _cls("patchify", "hbm", 1e9, peaks["hbm_gbs"]),
+        _cls("head", "hbm", 1e9, peaks["hbm_gbs"]),
+        _cls("attention", "tensor", 1e12, peaks["tflops"]),
+    ]
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
