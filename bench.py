@@ -217,7 +217,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py (impl ours) needs a GPU; there is no CPU fallback"
     device = torch.device("cuda", local_rank)
     from ovmr_b200 import _lib as L
-    from ovmr_b200.data import DevicePrefetcher
+    from ovmr_b200.data import DevicePrefetcher, plan_batches
     from ovmr_b200.config import precision
 
     C, S, Q, B = args.classes, args.shots, args.queries, args.batch
@@ -232,27 +232,6 @@ def main():
     ex_dev = device_images(n_ex_local, device, seed=1 + rank)
     q_dev = device_images(n_q_local, device, seed=1001 + rank)
     ex_labels = torch.arange(shard.lo, shard.hi, device=device).repeat_interleave(S)
-
-    def plan_batches(n, cap, unit=1):
-        """Split n items (each `unit` images) into batches of at most `cap` items.  Two candidates — full batches plus
-        a ragged tail, or ceil(n / cap) batches whose sizes differ by at most one — are compared with a wave model
-        of the persistent CTA-pair GEMMs (256 x 256 tiles over 74 SM pairs; QKV / out-proj / c_fc / c_proj of
-        ViT-B/16) and the cheaper one is used: a ragged tail costs whole waves, a slightly short batch may too."""
-        def cost(sizes):
-            c = 0
-            for z in sizes:
-                mp = -(-z * unit * 197 // 256)
-                c += sum(-(-mp * nt // 74) * k for nt, k in ((9, 1), (3, 1), (12, 1), (3, 4)))
-            return c
-        k = max(1, -(-n // cap))
-        base, extra = divmod(n, k)
-        even = [base + (1 if i < extra else 0) for i in range(k)]
-        ragged = [cap] * (n // cap) + ([n % cap] if n % cap else [])
-        sizes = even if cost(even) < cost(ragged) else ragged
-        offs = [0]
-        for z in sizes:
-            offs.append(offs[-1] + z)
-        return list(zip(offs[:-1], sizes))
 
     ex_plan = [(o * S, z * S) for o, z in plan_batches(shard.size, cls_per_batch, unit=S)]   # whole classes per batch
     q_plan = plan_batches(n_q_local, B)

@@ -231,7 +231,8 @@ int attention(const void* qkv, void* out, int n_seq, int L, int D, int heads, in
   const int nkb = (L + KB - 1) / KB;
   const size_t smem = (static_cast<size_t>(2) * nkb * KB + QT) * PITCH * 2;
   OVMR_REQUIRE(smem <= 227 * 1024, "attention: L=%d too long for the single-pass kernel", L);
-  static size_t configured = 0;
+  static PerDeviceSize configured_smem;
+  size_t& configured = configured_smem.cur();
   if (smem > configured) {
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

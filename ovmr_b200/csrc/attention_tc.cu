@@ -358,12 +358,11 @@ int attention_tc(const void* qkv, void* out, int n_seq, int L, int D, int heads,
   if (rc) return rc;
   const uint32_t kv_stride = (static_cast<uint32_t>(Lpad) * 128u + 1023u) & ~1023u;
   const size_t smem = 2 * Q_BYTES + 4 * static_cast<size_t>(kv_stride) + 8 * 17 + 16 + 1024 + 8 * 4096 + 1024;  // + output boxes
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     const int max_smem = 2 * Q_BYTES + 4 * 32768 + 8 * 17 + 16 + 1024 + 8 * 4096 + 1024;
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    configured = true;
   }
   const int n_work = n_seq * heads;
   const int grid = n_work < num_sms() ? n_work : num_sms();

@@ -31,6 +31,23 @@ int make_tmap_3d_16b(CUtensorMap* map, const void* base, long long d0, long long
 int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, long long rows, long long cols, long long ld,
                  int box_rows, int box_cols);
 
+// Kernel attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) are per DEVICE: call-site caches are indexed by the
+// current device so that a process driving several GPUs configures each of them.
+int current_device();   // 0..63 (clamped)
+struct PerDeviceOnce {
+  bool seen[64] = {};
+  bool first() {
+    const int d = current_device();
+    if (seen[d]) return false;
+    seen[d] = true;
+    return true;
+  }
+};
+struct PerDeviceSize {
+  size_t v[64] = {};
+  size_t& cur() { return v[current_device()]; }
+};
+
 // kernel classes for the optional device-side timing (see runtime.cu)
 enum ProfCat { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_ROWOPS = 3, PROF_HEAD = 4, PROF_NCAT = 5 };
 bool profiling();

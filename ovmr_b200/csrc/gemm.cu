@@ -701,11 +701,9 @@ int launch(const void* A, long long lda, const void* B, long long ldb, int M, in
   int rc = build_maps(mp, A, lda, B, ldb, M, N, K, ep, MODE, BLOCK_N);
   if (rc) return rc;
   auto kern = gemm_tn_kernel<BLOCK_N, MODE>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  static PerDeviceOnce attr;  // per template instantiation and device
+  if (attr.first())
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
@@ -723,11 +721,9 @@ int launch_pair(const void* A, long long lda, const void* B, long long ldb, int 
   int rc = build_maps(mp, A, lda, B, ldb, M, N, K, ep, MODE, Cfg::BLOCK_N / 2);
   if (rc) return rc;
   auto kern = gemm_tn_pair_kernel<MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr;
+  if (attr.first())
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
   const int m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
   const int total = m_pairs * n_tiles;
   const int max_clusters = num_sms() / 2;

@@ -172,8 +172,9 @@ int fusion_softmax_topk(const float* logits, long long rows, long long ld, int s
   OVMR_REQUIRE(rows <= 0x7fffffffLL, "fusion_softmax_topk: too many rows");
   const size_t smem = static_cast<size_t>(C) * sizeof(float);
   OVMR_REQUIRE(smem <= 200 * 1024, "fusion_softmax_topk: C=%d exceeds the shared-memory row buffer", C);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
+  static PerDeviceSize configured_smem;   // (0 = the 48 KB default)
+  size_t& configured = configured_smem.cur();
+  if (smem > 48 * 1024 && smem > configured) {
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(fusion_softmax_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }

@@ -164,6 +164,12 @@ int make_tmap_16b(CUtensorMap* map, const void* base, long long rows, long long 
   return make_tmap_2d(map, base, 2, rows, cols, ld, box_rows, 64);
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+  return dev < 64 ? dev : 63;
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;

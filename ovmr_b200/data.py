@@ -6,9 +6,37 @@ Image tensors land in a fixed ring of device buffers owned by the prefetcher (no
 allocator traffic in the loop): slot i % R is refilled only after the compute stream has passed the point
 where the batch that previously lived there was handed back (an event recorded when the NEXT batch is yielded).
 """
-from typing import Dict, Iterable, Iterator, List
+from typing import Dict, Iterable, Iterator, List, Tuple
 
 import torch
+
+
+def plan_batches(n: int, cap: int, unit: int = 1, tokens_per_image: int = 197, sm_pairs: int = 74) -> List[Tuple[int, int]]:
+    """Split n items (each `unit` images) into batches of at most `cap` items; returns (offset, size) pairs.
+    Two candidates — full batches plus a ragged tail, or ceil(n / cap) batches whose sizes differ by at most one —
+    are compared with a wave model of the persistent CTA-pair GEMMs (256 x 256 tiles over `sm_pairs` SM pairs; QKV /
+    out-proj / c_fc / c_proj of ViT-B/16) and the cheaper one is used: a ragged tail costs whole waves, a slightly
+    short batch may too."""
+    if n <= 0:
+        return []
+    cap = max(1, cap)
+
+    def cost(sizes):
+        c = 0
+        for z in sizes:
+            mp = -(-z * unit * tokens_per_image // 256)
+            c += sum(-(-mp * nt // sm_pairs) * k for nt, k in ((9, 1), (3, 1), (12, 1), (3, 4)))
+        return c
+    k = -(-n // cap)
+    base, extra = divmod(n, k)
+    even = [base + (1 if i < extra else 0) for i in range(k)]
+    ragged = [cap] * (n // cap) + ([n % cap] if n % cap else [])
+    sizes = even if cost(even) < cost(ragged) else ragged
+    out, off = [], 0
+    for z in sizes:
+        out.append((off, z))
+        off += z
+    return out
 
 
 class DevicePrefetcher:

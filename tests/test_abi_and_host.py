@@ -121,3 +121,16 @@ def test_shard_ranges_partition_exactly():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_plan_batches_partitions_exactly_and_respects_cap():
+    from ovmr_b200.data import plan_batches
+    for n, cap, unit in ((1000, 32, 16), (50000, 512, 1), (125, 32, 16), (6250, 512, 1), (1, 512, 1), (513, 512, 1),
+                         (21841, 128, 4), (0, 512, 1)):
+        plan = plan_batches(n, cap, unit)
+        assert sum(z for _, z in plan) == n
+        assert all(0 < z <= cap for _, z in plan)
+        off = 0
+        for o, z in plan:
+            assert o == off
+            off += z
