@@ -469,6 +469,34 @@ def forward_prompt(sd: State, pl: State, tokenized_prompts: Tensor, visual_templ
             "exemplar_preds": preds}
 
 
+def training_loss(sd: State, pl: State, tokenized_prompts: Tensor, visual_template_tokens: Tensor, images: Tensor,
+                  labels: Tensor, n_ins: int, split_point: int) -> Tensor:
+    """Training branch of CustomCLIP.forward (trainers/...:296-337) with dropout disabled: each class's n_ins images
+    are split at `split_point` into queries [:split_point] and exemplars [split_point:]; the exemplars drive the
+    visual token generator, the two prompt sets go through the frozen text tower, and the loss is
+    CE(mm logits) + CE(v logits) of the queries against the in-batch class index.  Differentiable w.r.t. `pl`
+    (cls_token and the aggregator weights): call torch.autograd.grad on the result.  SURVEY.md §8f.4 oracle."""
+    num_cls = images.shape[0] // n_ins
+    grouped = images.reshape(num_cls, n_ins, *images.shape[1:])
+    exemplar_image = grouped[:, split_point:n_ins].flatten(0, 1)
+    input_image = grouped[:, :split_point].flatten(0, 1)
+    logit_scale = sd["logit_scale"].exp()
+    with torch.no_grad():
+        image_features = l2n(encode_image(sd, input_image))
+        exemplar_features = l2n(encode_image(sd, exemplar_image)).reshape(num_cls, n_ins - split_point, -1)
+    exemplar_label = labels.reshape(num_cls, n_ins)[:, 0]
+    train_labels = torch.arange(num_cls).reshape(num_cls, -1).repeat(1, split_point).reshape(-1)
+    prompt_tokens = sd["token_embedding.weight"][tokenized_prompts.long()]
+    visual_prompt_temp = sd["token_embedding.weight"][visual_template_tokens.long()]
+    eot = tokenized_prompts[exemplar_label].argmax(dim=-1)
+    mm_p, mm_l, v_p, v_l, _ = prompt_learner_forward(pl, prompt_tokens, visual_prompt_temp, exemplar_features,
+                                                    exemplar_label, eot)
+    mm, v = get_mm_v_feats(sd, mm_p, mm_l, v_p, v_l)
+    mm_logits = (logit_scale * image_features @ mm.t()).float()
+    v_logits = (logit_scale * image_features @ v.t()).float()
+    return F.cross_entropy(mm_logits, train_labels) + F.cross_entropy(v_logits, train_labels)
+
+
 def classify(logit_scale: Tensor, image_features: Tensor, cls: dict, mode: str = "fusion") -> Tensor:
     """CustomCLIP.forward eval branch (trainers/...:348-363). image_features already normalised."""
     sm = lambda w: (logit_scale * image_features @ w.t()).float().softmax(dim=-1)

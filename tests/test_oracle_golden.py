@@ -121,3 +121,26 @@ def test_topk_ties_resolve_to_lowest_index():
     assert i1[:, 0].tolist() == [1, 0]
     i2, v2 = O.topk(p, 3)
     assert i2.tolist() == [[1, 2, 0], [0, 1, 2]]
+
+
+def test_training_branch_oracle_matches_reference_golden():
+    """SURVEY.md §8f.4 oracle: loss and gradients of the training branch (trainers/...:296-337, dropout off) from
+    torch autograd on the oracle restatement == the executed reference (oracle/gen_golden_training.py)."""
+    from ovmr_b200.clip import tokenize
+    g = _load("training_tiny")
+    n_cls, n_ins, split = int(g["n_cls"]), int(g["n_ins"]), int(g["split"])
+    cfg = O.CLIP_CONFIGS["tiny"]
+    sd = O.init_clip_state(cfg, seed=0)
+    pl = {k: v.clone().requires_grad_(True) for k, v in O.init_prompt_learner_state(cfg[0], n_ctx=2, seed=1).items()}
+    images = O.synth_images(n_cls * n_ins, cfg[1], seed=31)
+    labels = torch.arange(n_cls).repeat_interleave(n_ins)
+    tok = tokenize([f"a class {i}." for i in range(n_cls)])
+    loss = O.training_loss(sd, pl, tok, tokenize("a ."), images, labels, n_ins, split)
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-5
+    grads = dict(zip(pl, torch.autograd.grad(loss, list(pl.values()))))
+    names = [str(n) for n in g["grad_names"]]
+    norms = torch.tensor([float(grads[k].norm()) for k in names], dtype=torch.float64)
+    assert torch.allclose(norms, torch.from_numpy(g["grad_norms"]), rtol=1e-4, atol=1e-7)
+    for k in g.files:
+        if k.startswith("grad:"):
+            assert (grads[k[5:]] - torch.from_numpy(g[k])).abs().max() < 1e-5, k
