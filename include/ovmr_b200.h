@@ -208,6 +208,38 @@ int ovmr_f1_counts(const int* pred, const int* labels, long long rows, int nseg,
 /* F1 per class and classifier + softmax(tau*F1) (trainers/...:268-274). f1_out may be NULL. */
 int ovmr_fusion_weights(const int* counts, int nseg, int n_cls, float tau, float* f1_out, float* w_out, void* stream);
 
+/* ---------------------------------------------------------------- training branch
+ * Backward pieces of MM_CLS_OP.forward_backward (trainers/mm_classifier_one_prompt.py:296-337, 421-452): the loss is
+ * back-propagated through the frozen text tower into the visual tokens and on into the aggregator.  The matrix
+ * products of the backward pass are ovmr_gemm_tn calls on transposed operands (ovmr_transpose_16); the functions
+ * below are the remaining formulas (each checked against autograd by the test suite).  16-bit buffers are bf16 (fp16 = 0)
+ * or IEEE fp16. */
+/* LayerNorm backward: dy fp32 [rows, width] -> dx[src(r)] = dLN (+ dres[src(r)]), src(r) = r*gather_mul + gather[r]
+ * (gather NULL: src = r); dgamma / dbeta (fp32 [width], may be NULL) ACCUMULATE. */
+int ovmr_layernorm_backward(const float* x, int rows, int width, const int* gather, long long gather_mul,
+                            const float* gamma, const float* dy, const float* dres, float* dx, float* dgamma,
+                            float* dbeta, void* stream);
+/* du = dh * QuickGELU'(u): u, du 16-bit [n], dh fp32 [n]. */
+int ovmr_quickgelu_backward(const void* u, const float* dh, void* du, long long n, int fp16, void* stream);
+/* fp32 -> 16-bit cast (A operands of the gradient GEMMs). */
+int ovmr_cast_16(const float* x, void* out, long long n, int fp16, void* stream);
+/* out[c, r] = in[r, c]: in fp32 (in_is_f32) or 16-bit [rows, ld_in] -> 16-bit [cols, ld_out >= rows], zero padded. */
+int ovmr_transpose_16(const void* in, int in_is_f32, long long ld_in, int rows, int cols, void* out, long long ld_out,
+                      int fp16, void* stream);
+/* out[c] += sum_r in[r, c] (bias gradients); in fp32 or 16-bit. */
+int ovmr_colsum(const void* in, int in_is_f32, long long ld_in, int rows, int cols, float* out, int fp16, void* stream);
+/* y = x / ||x|| backward, fp32 [rows, width]. */
+int ovmr_l2norm_backward(const float* x, const float* dy, float* dx, int rows, int width, void* stream);
+/* F.cross_entropy (mean): *loss += -mean log softmax(logits)[label]; dlogits = (softmax - onehot) / rows. */
+int ovmr_cross_entropy(const float* logits, long long ld, const int* labels, int rows, int n_cls, float* loss,
+                       float* dlogits, long long ldd, void* stream);
+/* softmax-attention backward for short sequences (seq_len <= 96): qkv, dout, dqkv 16-bit as in ovmr_attention. */
+int ovmr_attention_backward(const void* qkv, const void* dout, void* dqkv, int n_seq, int seq_len, int width, int heads,
+                            int causal, int fp16, void* stream);
+/* torch.optim.Adam step on flat fp32 buffers (step counts from 1). */
+int ovmr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

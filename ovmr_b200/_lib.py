@@ -78,6 +78,17 @@ SIGNATURES = {
     "ovmr_argmax_segments": (c_int, [c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ovmr_f1_counts": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p]),
     "ovmr_fusion_weights": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "ovmr_layernorm_backward": (c_int, [c_void_p, c_int, c_int, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
+    "ovmr_quickgelu_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "ovmr_cast_16": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "ovmr_transpose_16": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_ll, c_int, c_void_p]),
+    "ovmr_colsum": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "ovmr_l2norm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "ovmr_cross_entropy": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p]),
+    "ovmr_attention_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ovmr_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
+                               c_int, c_void_p]),
 }
 
 _lib = None

@@ -3,9 +3,9 @@ generator), CustomCLIP (classifier generation + text / vision / multimodal / fus
 the MM_CLS_OP trainer shell — with the reference's names, arguments, buffers and artefact layout
 (trainers/mm_classifier_one_prompt.py of Zehong-Ma/OVMR), computing through the sm_100a C-ABI.
 
-Scope: the eval-mode hot path.  The training branch of CustomCLIP.forward /
-forward_backward (§8f.4) raises NotImplementedError.  Classifiers are kept in fp32 (the reference
-stores fp16 and converts to fp32 when saving `mm_classifiers.pt`).
+Scope: the eval-mode hot path plus the training branch of CustomCLIP.forward /
+forward_backward (§8f.4, ovmr_b200/training.py; dropout is not applied).  Classifiers are kept in fp32 (the
+reference stores fp16 and converts to fp32 when saving `mm_classifiers.pt`).
 """
 import os
 import os.path as osp
@@ -166,6 +166,15 @@ class CustomCLIP(nn.Module):
         self.fusion_weight = None
         self.device = clip_model.visual.conv1.weight.device
         self._banks = {}
+
+    def trainer(self, **adam):
+        """Native training state (bf16 operand copies, Adam moments) of the visual token generator."""
+        t = getattr(self, "_trainer", None)
+        if t is None:
+            from ..training import GeneratorTrainer
+            t = GeneratorTrainer(self, **adam)
+            object.__setattr__(self, "_trainer", t)
+        return t
 
     # ------------------------------------------------------------------ pieces
     def _vision(self) -> E.VisionEngine:
@@ -331,8 +340,13 @@ class CustomCLIP(nn.Module):
     def forward(self, image, label=None, eval_set_loader=None, scale_no=None):
         """trainers/...:294-364, eval branch: returns the [B, C] fp32 probabilities of cfg.EVAL_MODE."""
         if self.prompt_learner.training:
-            raise NotImplementedError("the training branch (random exemplar/query split + CE loss) is outside the "
-                                      "eval hot path this build covers (SURVEY.md §8f.4); call .eval() first")
+            # training branch (trainers/...:296-337): loss of the visual token generator.  Loss and gradients are
+            # computed natively (ovmr_b200.training); the returned tensor is wired into autograd so that the
+            # reference's `loss.backward(); optim.step()` works unchanged.
+            from ..training import _NativeLoss
+            tr = self.trainer()
+            names = list(tr.params)
+            return _NativeLoss.apply(tr, image, label, None, names, *[tr.params[n] for n in names])
         image_features = self._vision().encode(image.to(self.device), normalize=True)
         if self.mm_classifier is None:
             if eval_set_loader is None:
@@ -380,7 +394,19 @@ class MM_CLS_OP:
                 param.requires_grad_(False)
 
     def forward_backward(self, batch):
-        raise NotImplementedError("training of the visual token generator is outside this build's scope (§8f.4)")
+        """trainers/...:421-452: one optimisation step of the visual token generator (native loss, gradients and
+        Adam; cfg.OPTIM.LR / MAX_EPOCH drive the cosine schedule when present)."""
+        image, label = self.parse_batch_train(batch)
+        self.model.prompt_learner.train()
+        optim = getattr(self.cfg, "OPTIM", None)
+        base_lr = float(getattr(optim, "LR", 2e-4)) if optim is not None else 2e-4
+        tr = self.model.trainer(lr=base_lr)
+        lr = base_lr
+        if optim is not None and getattr(optim, "MAX_EPOCH", 0):
+            from ..training import cosine_lr
+            lr = cosine_lr(base_lr, int(getattr(self, "epoch", 0)), int(optim.MAX_EPOCH))
+        loss = tr.step(image, label, lr=lr)
+        return {"loss": loss}
 
     def parse_batch_train(self, batch):
         return batch["img"].to(self.device), batch["label"].to(self.device)
