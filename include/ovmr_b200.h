@@ -233,9 +233,19 @@ int ovmr_l2norm_backward(const float* x, const float* dy, float* dx, int rows, i
 /* F.cross_entropy (mean): *loss += -mean log softmax(logits)[label]; dlogits = (softmax - onehot) / rows. */
 int ovmr_cross_entropy(const float* logits, long long ld, const int* labels, int rows, int n_cls, float* loss,
                        float* dlogits, long long ldd, void* stream);
-/* softmax-attention backward for short sequences (seq_len <= 96): qkv, dout, dqkv 16-bit as in ovmr_attention. */
+/* softmax-attention backward for short sequences (seq_len <= 96): qkv, dout, dqkv 16-bit as in ovmr_attention.
+ * p_drop / seed: attention-probability dropout of nn.MultiheadAttention(dropout=p) in training mode
+ * (clip/model.py:223); the mask is a counter-based hash of (seed, sequence, head, query, key). */
 int ovmr_attention_backward(const void* qkv, const void* dout, void* dqkv, int n_seq, int seq_len, int width, int heads,
-                            int causal, int fp16, void* stream);
+                            int causal, int fp16, float p_drop, unsigned seed, void* stream);
+/* the matching forward: out = dropout(softmax(q k^T / 8 + mask)) v for short sequences (p_drop = 0: plain attention). */
+int ovmr_attention_dropout_forward(const void* qkv, void* out, int n_seq, int seq_len, int width, int heads, int causal,
+                                   int fp16, float p_drop, unsigned seed, void* stream);
+/* nn.Dropout in training mode with the same hashed masks (element i keeps with probability 1 - p, scaled 1/(1-p)):
+ * 16-bit y = x * mask (dropout2 after QuickGELU, clip/model.py:230), and fp32 out = resid + y * mask (dropout3 +
+ * residual add, :232, 249-250; resid may be NULL).  In place allowed. */
+int ovmr_dropout_16(const void* x, void* y, long long n, float p_drop, unsigned seed, int fp16, void* stream);
+int ovmr_dropout_add(const float* y, const float* resid, float* out, long long n, float p_drop, unsigned seed, void* stream);
 /* torch.optim.Adam step on flat fp32 buffers (step counts from 1). */
 int ovmr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, void* stream);

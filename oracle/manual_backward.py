@@ -169,3 +169,23 @@ def training_step_grads(sd, pl, tokenized_prompts, visual_template_tokens, image
     dagg_in, grads = transformer_backward(agg_in, pl, "aggregator.", a_layers, a_heads, False, dagg_out, want_wgrad=True)
     grads["cls_token"] = dagg_in[:, :n_ctx].sum(0)
     return loss, grads
+
+
+def masked_block_forward(x, w, prefix, heads, causal, m_attn, m_h, m_out):
+    """ResidualAttentionBlockWithDropout.forward in TRAINING mode (clip/model.py:219-252) with the three dropout masks
+    given explicitly (already scaled by 1 / (1 - p)): m_attn [n, heads, L, L] on the attention probabilities
+    (nn.MultiheadAttention(dropout=p)), m_h [n, L, 4D] after QuickGELU (dropout2), m_out [n, L, D] after c_proj
+    (dropout3).  Differentiable (torch.autograd is the reference for the CUDA backward with the same masks)."""
+    g = lambda k: w[prefix + k]
+    n, L, D = x.shape
+    a1 = O.layer_norm(x, g("ln_1.weight"), g("ln_1.bias"))
+    qkv = a1 @ g("attn.in_proj_weight").t() + g("attn.in_proj_bias")
+    q, k, v = (t.view(n, L, heads, 64).transpose(1, 2) for t in qkv.split(D, dim=-1))
+    s = (q @ k.transpose(-1, -2)) / 8.0
+    if causal:
+        s = s + torch.full((L, L), float("-inf")).triu_(1)
+    ao = ((torch.softmax(s, -1) * m_attn) @ v).transpose(1, 2).reshape(n, L, D)
+    x_mid = x + ao @ g("attn.out_proj.weight").t() + g("attn.out_proj.bias")
+    a2 = O.layer_norm(x_mid, g("ln_2.weight"), g("ln_2.bias"))
+    h = O.quick_gelu(a2 @ g("mlp.c_fc.weight").t() + g("mlp.c_fc.bias")) * m_h
+    return x_mid + (h @ g("mlp.c_proj.weight").t() + g("mlp.c_proj.bias")) * m_out

@@ -86,7 +86,12 @@ SIGNATURES = {
     "ovmr_colsum": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p]),
     "ovmr_l2norm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "ovmr_cross_entropy": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p]),
-    "ovmr_attention_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ovmr_attention_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                        C.c_uint, c_void_p]),
+    "ovmr_attention_dropout_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, C.c_uint,
+                                               c_void_p]),
+    "ovmr_dropout_16": (c_int, [c_void_p, c_void_p, c_ll, c_float, C.c_uint, c_int, c_void_p]),
+    "ovmr_dropout_add": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_float, C.c_uint, c_void_p]),
     "ovmr_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
                                c_int, c_void_p]),
 }

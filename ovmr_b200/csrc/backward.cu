@@ -28,6 +28,33 @@ __device__ __forceinline__ void st16(void* p, long long i, float v, int fp16) {
   else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
 }
 
+// ------------------------------------------------------------------ dropout (ResidualAttentionBlockWithDropout,
+// clip/model.py:219-252: attention-probability dropout inside nn.MultiheadAttention, dropout2 after QuickGELU,
+// dropout3 after c_proj).  Masks come from a counter-based hash of (seed, element index), so the backward pass
+// regenerates exactly the mask of the forward pass; kept elements are scaled by 1 / (1 - p).
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ float drop_scale(uint32_t seed, unsigned long long idx, float p) {
+  if (p <= 0.f) return 1.0f;
+  const uint32_t h = mix32(seed ^ mix32(static_cast<uint32_t>(idx) * 0x9e3779b9u + static_cast<uint32_t>(idx >> 32)));
+  const float u = (h >> 8) * (1.0f / 16777216.0f);          // [0, 1)
+  return u < p ? 0.f : 1.0f / (1.0f - p);
+}
+// y = x * mask (16-bit in / out; in place allowed)
+__global__ void dropout16_kernel(const void* x, void* y, long long n, float p, uint32_t seed, int fp16) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    st16(y, i, ld16(x, i, fp16) * drop_scale(seed, i, p), fp16);
+}
+// out = resid + y * mask   (fp32; resid may be NULL: out = y * mask; in place allowed)
+__global__ void dropout_add_kernel(const float* y, const float* resid, float* out, long long n, float p, uint32_t seed) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = (resid ? resid[i] : 0.f) + y[i] * drop_scale(seed, i, p);
+}
+
 // ------------------------------------------------------------------ LayerNorm backward
 // One warp per row.  Row r of dy belongs to source row src(r) = r * gather_mul + gather[r] of x (plain: src = r); dx is
 // written to the same row src(r) (+ dres[src(r)] when given).  dgamma / dbeta accumulate with atomics.
@@ -156,14 +183,17 @@ cross_entropy_kernel(const float* __restrict__ logits, long long ld, const int* 
   if (lane == 0) atomicAdd(loss, (logf(s) + m - lr[lab]) * invR);
 }
 
-// ------------------------------------------------------------------ attention backward, one CTA per (sequence, head)
-// qkv / dout / dqkv are 16-bit [n_seq * L, 3D] / [n_seq * L, D] / [n_seq * L, 3D]; head dim 64; L <= 96.
+// ------------------------------------------------------------------ short-sequence attention with dropout:
+// forward (dout == NULL: out = dropout(softmax(q k^T / 8 + mask)) v) and backward, one CTA per (sequence, head).
+// qkv / dqkv are 16-bit [n_seq * L, 3D], out / dout 16-bit [n_seq * L, D]; head dim 64; L <= 96.  The dropout mask of
+// probability (seq, head, i, j) is hashed from ((seq * heads + head) * L + i) * L + j.
 __global__ void __launch_bounds__(128)
-attention_backward_kernel(const void* __restrict__ qkv, const void* __restrict__ dout, void* __restrict__ dqkv, int L,
-                          int D, int causal, int fp16) {
+attention_small_kernel(const void* __restrict__ qkv, const void* __restrict__ dout, void* __restrict__ out_or_dqkv, int L,
+                       int D, int causal, int fp16, float p_drop, uint32_t seed) {
   extern __shared__ float sm[];
   const int h = blockIdx.x, seq = blockIdx.y, tid = threadIdx.x;
   const int P64 = 65;                       // padded row pitch of the [L][64] tiles
+  const bool bwd = dout != nullptr;
   float* q = sm;
   float* k = q + L * P64;
   float* v = k + L * P64;
@@ -171,28 +201,29 @@ attention_backward_kernel(const void* __restrict__ qkv, const void* __restrict__
   float* p = dO + L * P64;                  // [L][L+1] probabilities, later dS
   float* dp = p + L * (L + 1);              // [L][L+1]
   const long long row0 = static_cast<long long>(seq) * L;
+  const unsigned long long mask0 = (static_cast<unsigned long long>(seq) * gridDim.x + h) * L * L;
   for (int i = tid; i < L * 64; i += 128) {
     const int r = i >> 6, d = i & 63;
     const long long base = (row0 + r) * 3LL * D + h * 64 + d;
     q[r * P64 + d] = ld16(qkv, base, fp16);
     k[r * P64 + d] = ld16(qkv, base + D, fp16);
     v[r * P64 + d] = ld16(qkv, base + 2LL * D, fp16);
-    dO[r * P64 + d] = ld16(dout, (row0 + r) * static_cast<long long>(D) + h * 64 + d, fp16);
+    if (bwd) dO[r * P64 + d] = ld16(dout, (row0 + r) * static_cast<long long>(D) + h * 64 + d, fp16);
   }
   __syncthreads();
-  // S = q k^T / 8 (+ mask) and dP = dO v^T
+  // S = q k^T / 8 (+ mask) and dP' = dO v^T
   for (int i = tid; i < L * L; i += 128) {
     const int r = i / L, c = i % L;
     float s = 0.f, t = 0.f;
     for (int d = 0; d < 64; ++d) {
       s += q[r * P64 + d] * k[c * P64 + d];
-      t += dO[r * P64 + d] * v[c * P64 + d];
+      if (bwd) t += dO[r * P64 + d] * v[c * P64 + d];
     }
     p[r * (L + 1) + c] = (causal && c > r) ? -INFINITY : s * 0.125f;
     dp[r * (L + 1) + c] = t;
   }
   __syncthreads();
-  // row softmax, then dS = P * (dP - sum_j dP P)   (one thread per row: L <= 96)
+  // row softmax; backward: dS = P * (dP - sum_j dP P) with dP = dP' * mask   (one thread per row: L <= 96)
   for (int r = tid; r < L; r += 128) {
     float m = -INFINITY;
     for (int c = 0; c < L; ++c) m = fmaxf(m, p[r * (L + 1) + c]);
@@ -206,24 +237,38 @@ attention_backward_kernel(const void* __restrict__ qkv, const void* __restrict__
     float dot = 0.f;
     for (int c = 0; c < L; ++c) {
       p[r * (L + 1) + c] *= inv;
-      dot += p[r * (L + 1) + c] * dp[r * (L + 1) + c];
+      if (bwd) {
+        dp[r * (L + 1) + c] *= drop_scale(seed, mask0 + static_cast<unsigned long long>(r) * L + c, p_drop);
+        dot += p[r * (L + 1) + c] * dp[r * (L + 1) + c];
+      }
     }
-    for (int c = 0; c < L; ++c) dp[r * (L + 1) + c] = p[r * (L + 1) + c] * (dp[r * (L + 1) + c] - dot);   // dS
+    if (bwd)
+      for (int c = 0; c < L; ++c) dp[r * (L + 1) + c] = p[r * (L + 1) + c] * (dp[r * (L + 1) + c] - dot);   // dS
   }
   __syncthreads();
-  // dV = P^T dO, dQ = dS k / 8, dK = dS^T q / 8
+  if (!bwd) {   // out = (P * mask) v
+    for (int i = tid; i < L * 64; i += 128) {
+      const int r = i >> 6, d = i & 63;
+      float o = 0.f;
+      for (int c = 0; c < L; ++c)
+        o += p[r * (L + 1) + c] * drop_scale(seed, mask0 + static_cast<unsigned long long>(r) * L + c, p_drop) * v[c * P64 + d];
+      st16(out_or_dqkv, (row0 + r) * static_cast<long long>(D) + h * 64 + d, o, fp16);
+    }
+    return;
+  }
+  // dV = (P * mask)^T dO, dQ = dS k / 8, dK = dS^T q / 8
   for (int i = tid; i < L * 64; i += 128) {
     const int r = i >> 6, d = i & 63;
     float dv = 0.f, dq = 0.f, dk = 0.f;
     for (int c = 0; c < L; ++c) {
-      dv += p[c * (L + 1) + r] * dO[c * P64 + d];
+      dv += p[c * (L + 1) + r] * drop_scale(seed, mask0 + static_cast<unsigned long long>(c) * L + r, p_drop) * dO[c * P64 + d];
       dq += dp[r * (L + 1) + c] * k[c * P64 + d];
       dk += dp[c * (L + 1) + r] * q[c * P64 + d];
     }
     const long long base = (row0 + r) * 3LL * D + h * 64 + d;
-    st16(dqkv, base, dq * 0.125f, fp16);
-    st16(dqkv, base + D, dk * 0.125f, fp16);
-    st16(dqkv, base + 2LL * D, dv, fp16);
+    st16(out_or_dqkv, base, dq * 0.125f, fp16);
+    st16(out_or_dqkv, base + D, dk * 0.125f, fp16);
+    st16(out_or_dqkv, base + 2LL * D, dv, fp16);
   }
 }
 
@@ -309,17 +354,46 @@ int ovmr_cross_entropy(const float* logits, long long ld, const int* labels, int
   return 0;
 }
 
-int ovmr_attention_backward(const void* qkv, const void* dout, void* dqkv, int n_seq, int seq_len, int width, int heads,
-                            int causal, int fp16, void* stream) {
-  OVMR_REQUIRE(qkv && dout && dqkv && n_seq > 0 && seq_len > 0 && width == heads * 64, "attention_backward: bad arguments");
-  OVMR_REQUIRE(seq_len <= 96, "attention_backward: seq_len=%d exceeds the short-sequence kernel (<= 96)", seq_len);
+static int attention_small(const void* qkv, const void* dout, void* out, int n_seq, int seq_len, int width, int heads,
+                           int causal, int fp16, float p_drop, unsigned seed, void* stream, const char* what) {
+  OVMR_REQUIRE(qkv && out && n_seq > 0 && seq_len > 0 && width == heads * 64, "%s: bad arguments", what);
+  OVMR_REQUIRE(seq_len <= 96, "%s: seq_len=%d exceeds the short-sequence kernel (<= 96)", what, seq_len);
+  OVMR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "%s: dropout probability %f", what, p_drop);
   const size_t smem = (4ull * seq_len * 65 + 2ull * seq_len * (seq_len + 1)) * sizeof(float);
   static ovmr::PerDeviceSize configured;
   if (smem > 48 * 1024 && smem > configured.cur()) {
-    OVMR_CHECK_CUDA(cudaFuncSetAttribute(attention_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OVMR_CHECK_CUDA(cudaFuncSetAttribute(attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured.cur() = smem;
   }
-  attention_backward_kernel<<<dim3(heads, n_seq), 128, smem, S(stream)>>>(qkv, dout, dqkv, seq_len, width, causal, fp16);
+  attention_small_kernel<<<dim3(heads, n_seq), 128, smem, S(stream)>>>(qkv, dout, out, seq_len, width, causal, fp16, p_drop, seed);
+  OVMR_CHECK_CUDA(cudaGetLastError());
+  ovmr::count_launches(1);
+  return 0;
+}
+
+int ovmr_attention_backward(const void* qkv, const void* dout, void* dqkv, int n_seq, int seq_len, int width, int heads,
+                            int causal, int fp16, float p_drop, unsigned seed, void* stream) {
+  OVMR_REQUIRE(dout != nullptr, "attention_backward: null dout");
+  return attention_small(qkv, dout, dqkv, n_seq, seq_len, width, heads, causal, fp16, p_drop, seed, stream, "attention_backward");
+}
+
+int ovmr_attention_dropout_forward(const void* qkv, void* out, int n_seq, int seq_len, int width, int heads, int causal,
+                                   int fp16, float p_drop, unsigned seed, void* stream) {
+  return attention_small(qkv, nullptr, out, n_seq, seq_len, width, heads, causal, fp16, p_drop, seed, stream,
+                         "attention_dropout_forward");
+}
+
+int ovmr_dropout_16(const void* x, void* y, long long n, float p_drop, unsigned seed, int fp16, void* stream) {
+  OVMR_REQUIRE(x && y && n > 0 && p_drop >= 0.f && p_drop < 1.f, "dropout_16: bad arguments");
+  dropout16_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(x, y, n, p_drop, seed, fp16);
+  OVMR_CHECK_CUDA(cudaGetLastError());
+  ovmr::count_launches(1);
+  return 0;
+}
+
+int ovmr_dropout_add(const float* y, const float* resid, float* out, long long n, float p_drop, unsigned seed, void* stream) {
+  OVMR_REQUIRE(y && out && n > 0 && p_drop >= 0.f && p_drop < 1.f, "dropout_add: bad arguments");
+  dropout_add_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(y, resid, out, n, p_drop, seed);
   OVMR_CHECK_CUDA(cudaGetLastError());
   ovmr::count_launches(1);
   return 0;

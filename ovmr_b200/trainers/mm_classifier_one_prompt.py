@@ -4,7 +4,7 @@ the MM_CLS_OP trainer shell — with the reference's names, arguments, buffers a
 (trainers/mm_classifier_one_prompt.py of Zehong-Ma/OVMR), computing through the sm_100a C-ABI.
 
 Scope: the eval-mode hot path plus the training branch of CustomCLIP.forward /
-forward_backward (§8f.4, ovmr_b200/training.py; dropout is not applied).  Classifiers are kept in fp32 (the
+forward_backward (§8f.4, ovmr_b200/training.py).  Classifiers are kept in fp32 (the
 reference stores fp16 and converts to fp32 when saving `mm_classifiers.pt`).
 """
 import os

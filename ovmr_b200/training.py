@@ -11,11 +11,11 @@ Backward design: only the INPUT of every residual block is kept; a block's backw
 eval kernels (LayerNorm, tcgen05 GEMMs, attention) and applies the hand-derived formulas of csrc/backward.cu.  All
 matrix products of the backward pass are `ovmr_gemm_tn` calls: dgrad on pre-transposed weights, wgrad on transposed
 activations.  Training operands are bf16 (fp32 accumulation, fp32 master weights and optimiser state).
-Dropout (aggregator, p = 0.1 in the reference) is NOT applied: the step is deterministic.
+The aggregator's dropout (p = 0.1 in the reference: attention probabilities, after QuickGELU, after c_proj) uses
+counter-based hashed masks regenerated identically in the backward pass.
 """
 import ctypes as C
 import math
-import warnings
 from typing import Dict, List, Optional
 
 import torch
@@ -70,8 +70,10 @@ class TowerState:
     eval path packs them), their transposes for dgrad, and the fp32 vectors.  `trainable` towers also produce
     parameter gradients and are re-packed from the fp32 masters after every optimiser step."""
 
-    def __init__(self, module, device, trainable: bool, prefix: str):
+    def __init__(self, module, device, trainable: bool, prefix: str, p_drop: float = 0.0):
         self.module, self.device, self.trainable, self.prefix = module, device, trainable, prefix
+        self.p_drop = float(p_drop)   # dropout probability in training mode (0 for the frozen towers)
+        self.seed = 0                 # re-drawn by the trainer every step
         self.width = int(module.width)
         self.blocks = list(module.resblocks)
         self.heads = int(self.blocks[0].attn.num_heads)
@@ -101,21 +103,14 @@ class TowerState:
                                       C.cast(C.byref(self.arr, i * C.sizeof(L.BlockWeights)), C.POINTER(L.BlockWeights)))
                         for i in range(n)]
 
-    # ---- forward keeping each block's input
-    def forward_save(self, x: torch.Tensor, n_seq: int, seq_len: int, causal: bool) -> List[torch.Tensor]:
-        lib = L.lib()
-        rows = n_seq * seq_len
-        buf = self.ws.get(lib.ovmr_transformer_workspace_bytes(rows, self.width))
-        saved = []
-        for st in self.structs:
-            saved.append(x.clone())
-            L.check(lib.ovmr_transformer_forward(C.byref(st), x.data_ptr(), n_seq, seq_len, int(causal), buf.data_ptr(),
-                                                 buf.numel(), L.stream()), "ovmr_transformer_forward")
-        return saved
+    # ---- dropout (ResidualAttentionBlockWithDropout in training mode): hashed masks, identical in forward and backward
+    def _seed(self, i: int, site: int) -> int:
+        return (self.seed * 0x9E3779B1 + 97 * i + site) & 0xFFFFFFFF
 
-    # ---- one block: recompute the forward from x_in, then the hand-derived backward
-    def _block_backward(self, i: int, x_in, n_seq, seq_len, causal, dy, grads: Optional[Dict[str, torch.Tensor]]):
-        lib, w, D, H = L.lib(), self.layers[i], self.width, self.heads
+    def _block_internals(self, i: int, x_in, n_seq, seq_len, causal, need_h: bool):
+        """Forward of block i from its input with the eval kernels (+ dropout when p_drop > 0): returns every
+        intermediate the backward needs and the block output."""
+        lib, w, D, H, p = L.lib(), self.layers[i], self.width, self.heads, self.p_drop
         rows, dev, st = n_seq * seq_len, x_in.device, L.stream()
         e16 = lambda r, c: torch.empty(r, c, dtype=BF16, device=dev)
         e32 = lambda r, c: torch.empty(r, c, dtype=F32, device=dev)
@@ -123,21 +118,71 @@ class TowerState:
         L.check(lib.ovmr_layernorm(x_in.data_ptr(), D, rows, D, None, 0, w["ln1_w"].data_ptr(), w["ln1_b"].data_ptr(), None, 0,
                                    a1.data_ptr(), D, None, None, FP16_FLAG, st), "ovmr_layernorm")
         _gemm(a1, D, w["qkv_w"], D, rows, 3 * D, D, qkv, 3 * D, bias=w["qkv_b"], out16=True)
-        L.check(lib.ovmr_attention(qkv.data_ptr(), ao.data_ptr(), n_seq, seq_len, D, H, int(causal), FP16_FLAG, st), "ovmr_attention")
+        if p > 0:
+            L.check(lib.ovmr_attention_dropout_forward(qkv.data_ptr(), ao.data_ptr(), n_seq, seq_len, D, H, int(causal), FP16_FLAG,
+                                                       p, self._seed(i, 0), st), "ovmr_attention_dropout_forward")
+        else:
+            L.check(lib.ovmr_attention(qkv.data_ptr(), ao.data_ptr(), n_seq, seq_len, D, H, int(causal), FP16_FLAG, st), "ovmr_attention")
         _gemm(ao, D, w["out_w"], D, rows, D, D, x_mid, D, bias=w["out_b"], resid=x_in, ldr=D)
         L.check(lib.ovmr_layernorm(x_mid.data_ptr(), D, rows, D, None, 0, w["ln2_w"].data_ptr(), w["ln2_b"].data_ptr(), None, 0,
                                    a2.data_ptr(), D, None, None, FP16_FLAG, st), "ovmr_layernorm")
         _gemm(a2, D, w["fc_w"], D, rows, 4 * D, D, u, 4 * D, bias=w["fc_b"], out16=True, act=0)
-        # ---- MLP
-        dy16 = _cast16(dy)
+        h = None
+        if need_h:
+            h = e16(rows, 4 * D)
+            _gemm(a2, D, w["fc_w"], D, rows, 4 * D, D, h, 4 * D, bias=w["fc_b"], out16=True, act=1)
+            if p > 0:   # dropout2
+                L.check(lib.ovmr_dropout_16(h.data_ptr(), h.data_ptr(), h.numel(), p, self._seed(i, 1), FP16_FLAG, st), "ovmr_dropout_16")
+        return a1, qkv, ao, x_mid, a2, u, h
+
+    def _block_forward_dropout(self, i: int, x, n_seq, seq_len, causal):
+        """x <- block_i(x) in training mode with dropout (in place)."""
+        lib, w, D, p, st = L.lib(), self.layers[i], self.width, self.p_drop, L.stream()
+        rows = n_seq * seq_len
+        _, _, _, x_mid, _, _, h = self._block_internals(i, x, n_seq, seq_len, causal, need_h=True)
+        y = torch.empty(rows, D, dtype=F32, device=x.device)
+        _gemm(h, 4 * D, w["proj_w"], 4 * D, rows, D, 4 * D, y, D, bias=w["proj_b"])
+        L.check(lib.ovmr_dropout_add(y.data_ptr(), x_mid.data_ptr(), x.data_ptr(), x.numel(), p, self._seed(i, 2), st),
+                "ovmr_dropout_add")   # dropout3 + residual
+
+    # ---- forward keeping each block's input
+    def forward_save(self, x: torch.Tensor, n_seq: int, seq_len: int, causal: bool) -> List[torch.Tensor]:
+        lib = L.lib()
+        rows = n_seq * seq_len
+        buf = self.ws.get(lib.ovmr_transformer_workspace_bytes(rows, self.width))
+        saved = []
+        for i, st in enumerate(self.structs):
+            saved.append(x.clone())
+            if self.p_drop > 0:
+                self._block_forward_dropout(i, x, n_seq, seq_len, causal)
+            else:
+                L.check(lib.ovmr_transformer_forward(C.byref(st), x.data_ptr(), n_seq, seq_len, int(causal), buf.data_ptr(),
+                                                     buf.numel(), L.stream()), "ovmr_transformer_forward")
+        return saved
+
+    # ---- one block: recompute the forward from x_in, then the hand-derived backward
+    def _block_backward(self, i: int, x_in, n_seq, seq_len, causal, dy, grads: Optional[Dict[str, torch.Tensor]]):
+        lib, w, D, H, p = L.lib(), self.layers[i], self.width, self.heads, self.p_drop
+        rows, dev, st = n_seq * seq_len, x_in.device, L.stream()
+        e16 = lambda r, c: torch.empty(r, c, dtype=BF16, device=dev)
+        e32 = lambda r, c: torch.empty(r, c, dtype=F32, device=dev)
+        want = grads is not None
+        a1, qkv, ao, x_mid, a2, u, h = self._block_internals(i, x_in, n_seq, seq_len, causal, need_h=want)
+        # ---- MLP (dropout3 masks the gradient entering c_proj, dropout2 the one entering QuickGELU)
+        dyp = dy
+        if p > 0:
+            dyp = e32(rows, D)
+            L.check(lib.ovmr_dropout_add(dy.data_ptr(), None, dyp.data_ptr(), dy.numel(), p, self._seed(i, 2), st), "ovmr_dropout_add")
+        dy16 = _cast16(dyp)
         dh = e32(rows, 4 * D)
         _gemm(dy16, D, w["proj_wT"], D, rows, 4 * D, D, dh, 4 * D)
+        if p > 0:
+            L.check(lib.ovmr_dropout_add(dh.data_ptr(), None, dh.data_ptr(), dh.numel(), p, self._seed(i, 1), st), "ovmr_dropout_add")
         du = e16(rows, 4 * D)
         L.check(lib.ovmr_quickgelu_backward(u.data_ptr(), dh.data_ptr(), du.data_ptr(), du.numel(), FP16_FLAG, st),
                 "ovmr_quickgelu_backward")
         da2 = e32(rows, D)
         _gemm(du, 4 * D, w["fc_wT"], 4 * D, rows, D, 4 * D, da2, D)
-        want = grads is not None
         z = lambda n: torch.zeros(n, dtype=F32, device=dev) if want else None
         dg2, db2, dg1, db1 = z(D), z(D), z(D), z(D)
         dx_mid = e32(rows, D)
@@ -148,15 +193,13 @@ class TowerState:
         _gemm(dxm16, D, w["out_wT"], D, rows, D, D, dao, D, out16=True)
         dqkv = e16(rows, 3 * D)
         L.check(lib.ovmr_attention_backward(qkv.data_ptr(), dao.data_ptr(), dqkv.data_ptr(), n_seq, seq_len, D, H, int(causal),
-                                            FP16_FLAG, st), "ovmr_attention_backward")
+                                            FP16_FLAG, p, self._seed(i, 0), st), "ovmr_attention_backward")
         da1 = e32(rows, D)
         _gemm(dqkv, 3 * D, w["qkv_wT"], 3 * D, rows, D, 3 * D, da1, D)
         dx_in = e32(rows, D)
         _ln_backward(x_in, rows, D, w["ln1_w"], da1, dx_in, dres=dx_mid, dgamma=dg1, dbeta=db1)
         if want:
-            h = e16(rows, 4 * D)
-            _gemm(a2, D, w["fc_w"], D, rows, 4 * D, D, h, 4 * D, bias=w["fc_b"], out16=True, act=1)
-            p = f"{self.prefix}resblocks.{i}."
+            pfx = f"{self.prefix}resblocks.{i}."
 
             def wgrad(dy_mat, n_out, x_mat, n_in):      # dW[n_out, n_in] = dY^T X
                 a, rp = _transpose16(dy_mat, rows, n_out)
@@ -164,16 +207,16 @@ class TowerState:
                 out = e32(n_out, n_in)
                 _gemm(a, rp, b, rp, n_out, n_in, rp, out, n_in)
                 return out
-            grads[p + "mlp.c_proj.weight"] = wgrad(dy, D, h, 4 * D)
-            grads[p + "mlp.c_proj.bias"] = _colsum(dy, rows, D)
-            grads[p + "mlp.c_fc.weight"] = wgrad(du, 4 * D, a2, D)
-            grads[p + "mlp.c_fc.bias"] = _colsum(du, rows, 4 * D)
-            grads[p + "ln_2.weight"], grads[p + "ln_2.bias"] = dg2, db2
-            grads[p + "attn.out_proj.weight"] = wgrad(dx_mid, D, ao, D)
-            grads[p + "attn.out_proj.bias"] = _colsum(dx_mid, rows, D)
-            grads[p + "attn.in_proj_weight"] = wgrad(dqkv, 3 * D, a1, D)
-            grads[p + "attn.in_proj_bias"] = _colsum(dqkv, rows, 3 * D)
-            grads[p + "ln_1.weight"], grads[p + "ln_1.bias"] = dg1, db1
+            grads[pfx + "mlp.c_proj.weight"] = wgrad(dyp, D, h, 4 * D)
+            grads[pfx + "mlp.c_proj.bias"] = _colsum(dyp, rows, D)
+            grads[pfx + "mlp.c_fc.weight"] = wgrad(du, 4 * D, a2, D)
+            grads[pfx + "mlp.c_fc.bias"] = _colsum(du, rows, 4 * D)
+            grads[pfx + "ln_2.weight"], grads[pfx + "ln_2.bias"] = dg2, db2
+            grads[pfx + "attn.out_proj.weight"] = wgrad(dx_mid, D, ao, D)
+            grads[pfx + "attn.out_proj.bias"] = _colsum(dx_mid, rows, D)
+            grads[pfx + "attn.in_proj_weight"] = wgrad(dqkv, 3 * D, a1, D)
+            grads[pfx + "attn.in_proj_bias"] = _colsum(dqkv, rows, 3 * D)
+            grads[pfx + "ln_1.weight"], grads[pfx + "ln_1.bias"] = dg1, db1
         return dx_in
 
     def backward(self, saved, n_seq, seq_len, causal, dy, grads=None):
@@ -185,17 +228,19 @@ class TowerState:
 class GeneratorTrainer:
     """Loss, gradients and Adam step of the visual token generator of a `CustomCLIP` (native; see module docstring)."""
 
-    def __init__(self, custom_clip, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+    def __init__(self, custom_clip, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 dropout: Optional[float] = None, seed: int = 0):
         self.m = custom_clip
         self.device = custom_clip.device
         clip_model = custom_clip.text_encoder._clip
         self.clip = clip_model
         pl = custom_clip.prompt_learner
-        if float(getattr(pl.aggregator, "dropout", 0.0)) > 0:
-            warnings.warn("ovmr_b200 training step: aggregator dropout is not applied (deterministic step)")
         dev = self.device
         self.text = TowerState(clip_model.transformer, dev, trainable=False, prefix="transformer.")
-        self.agg = TowerState(pl.aggregator, dev, trainable=True, prefix="aggregator.")
+        # TransformerDropout(dropout=0.1) in the reference (trainers/...:138-143); `dropout=` overrides
+        p_drop = float(getattr(pl.aggregator, "dropout", 0.0)) if dropout is None else float(dropout)
+        self.agg = TowerState(pl.aggregator, dev, trainable=True, prefix="aggregator.", p_drop=p_drop)
+        self.rng = torch.Generator().manual_seed(int(seed))
         self.text_engine = clip_model.text_engine(dev)
         self.keep = dict(pos=self.text_engine.keep["pos"],
                          lnf_w=clip_model.ln_final.weight.detach().to(dev, F32).contiguous(),
@@ -259,6 +304,7 @@ class GeneratorTrainer:
         num_cls = image.shape[0] // n_ins
         if split_point is None:      # trainers/...:301
             split_point = int(torch.randint(n_ins // 4, 3 * n_ins // 4, (1,))[0])
+        self.agg.seed = int(torch.randint(0, 2 ** 31 - 1, (1,), generator=self.rng)[0])   # fresh dropout masks per step
         image = image.to(dev)
         grouped = image.reshape(num_cls, n_ins, *image.shape[1:])
         vis = m.image_encoder.engine(dev)

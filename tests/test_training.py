@@ -130,7 +130,7 @@ def test_backward_kernels_match_hand_derived_formulas():
         ref = MB.attention_backward(qkv.float(), do.float(), heads, bool(causal))
         QKV, DO = qkv.to(DEV), do.to(DEV)
         dqkv = torch.empty_like(QKV)
-        L.check(lib.ovmr_attention_backward(QKV.data_ptr(), DO.data_ptr(), dqkv.data_ptr(), n_seq, Lq, D, heads, causal, 0, st))
+        L.check(lib.ovmr_attention_backward(QKV.data_ptr(), DO.data_ptr(), dqkv.data_ptr(), n_seq, Lq, D, heads, causal, 0, 0.0, 0, st))
         assert (dqkv.cpu().float() - ref).abs().max() < 2e-2 * max(1.0, float(ref.abs().max()))
         assert _cos(dqkv, ref) > 0.9995
     # ---- l2norm backward, cross-entropy
@@ -178,7 +178,7 @@ def test_native_training_step_matches_oracle_autograd():
     model = pair.model
     model.num_ins = n_ins
     model.prompt_learner.train()
-    tr = model.trainer(lr=1e-3)
+    tr = model.trainer(lr=1e-3, dropout=0.0)     # the oracle has no dropout; dropout is tested with explicit masks below
     loss, grads = tr.loss_and_grads(images.to(DEV), labels.to(DEV), split_point=split)
     torch.cuda.synchronize()
     plr = {k: v.clone().requires_grad_(True) for k, v in pl.items()}
@@ -201,4 +201,88 @@ def test_native_training_step_matches_oracle_autograd():
     for _ in range(5):
         last = tr.step(images.to(DEV), labels.to(DEV), split_point=split)
     assert last < first
+    model.prompt_learner.eval()
+
+
+@pytest.mark.gpu
+def test_dropout_masks_and_training_block_with_dropout_match_autograd():
+    """Training-mode dropout (hashed masks): mask statistics and determinism; then one aggregator block in training
+    mode — forward output and every gradient — against torch.autograd on the same block with the SAME masks (read
+    back from the kernels: dropout2 / dropout3 on all-ones inputs, attention masks through one-hot values)."""
+    import ctypes as C
+    from ovmr_b200 import _lib as L
+    from ovmr_b200.clip.model import TransformerDropout
+    from ovmr_b200.training import TowerState
+    lib, st = L.lib(), L.stream()
+    p = 0.25
+    ones = torch.ones(200000, dtype=torch.bfloat16, device=DEV)
+    m1, m2, m3 = torch.empty_like(ones), torch.empty_like(ones), torch.empty_like(ones)
+    for out, seed in ((m1, 11), (m2, 11), (m3, 12)):
+        L.check(lib.ovmr_dropout_16(ones.data_ptr(), out.data_ptr(), ones.numel(), p, seed, 0, st))
+    torch.cuda.synchronize()
+    assert torch.equal(m1, m2) and not torch.equal(m1, m3)
+    keep = (m1 > 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 0.01
+    assert set(m1.float().unique().tolist()) == {0.0, float(torch.tensor(1 / (1 - p)).bfloat16())}
+    # ---- one block of a TransformerDropout(width 128, 2 heads) in training mode
+    torch.manual_seed(3)
+    width, heads, n, Lq = 128, 2, 5, 7
+    mod = TransformerDropout(width=width, layers=1, heads=heads, dropout=p)
+    with torch.no_grad():
+        for prm in mod.parameters():
+            prm.copy_((prm + 0.05 * torch.randn_like(prm)).bfloat16().float())
+    tower = TowerState(mod.to(DEV), torch.device(DEV), trainable=True, prefix="aggregator.", p_drop=p)
+    tower.seed = 777
+    w = {"aggregator." + k: v.detach().cpu() for k, v in mod.state_dict().items()}
+    rows = n * Lq
+    # masks: dropout2 / dropout3 from the kernels on all-ones, attention masks through one-hot values
+    def mask16(numel, site):
+        o = torch.ones(numel, dtype=torch.bfloat16, device=DEV)
+        L.check(lib.ovmr_dropout_16(o.data_ptr(), o.data_ptr(), numel, p, tower._seed(0, site), 0, st))
+        return (o.float() > 0).float().cpu() / (1 - p)
+    m_h = mask16(rows * 4 * width, 1).view(n, Lq, 4 * width)
+    m_out = mask16(rows * width, 2).view(n, Lq, width)
+    qkv1 = torch.zeros(n, Lq, 3 * width)
+    for hh in range(heads):
+        for j in range(Lq):
+            qkv1[:, j, 2 * width + hh * 64 + j] = 1.0          # v_j = e_j: out[i, j] = P'[i, j]
+    Q1 = qkv1.bfloat16().to(DEV)
+    o1 = torch.empty(n, Lq, width, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.ovmr_attention_dropout_forward(Q1.data_ptr(), o1.data_ptr(), n, Lq, width, heads, 0, 0, p, tower._seed(0, 0), st))
+    pp = o1.float().cpu().view(n, Lq, heads, 64)[..., :Lq].permute(0, 2, 1, 3)      # [n, heads, L, L] = mask / (L (1 - p))
+    m_attn = (pp > 0).float() / (1 - p)
+    assert abs(float((m_attn > 0).float().mean()) - (1 - p)) < 0.15
+    # ---- forward + backward, native vs autograd with the same masks
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(n, Lq, width, generator=g)
+    dy = torch.randn(n, Lq, width, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    yr = MB.masked_block_forward(xr, wr, "aggregator.resblocks.0.", heads, False, m_attn, m_h, m_out)
+    gr = torch.autograd.grad(yr, [xr] + list(wr.values()), dy)
+    ref = dict(zip(["x"] + list(wr), gr))
+    X = x.view(rows, width).to(DEV).contiguous()
+    saved = tower.forward_save(X, n, Lq, False)
+    assert _cos(X, yr.detach().view(rows, width)) > 0.9995
+    grads = {}
+    dx = tower.backward(saved, n, Lq, False, dy.view(rows, width).to(DEV).contiguous(), grads)
+    torch.cuda.synchronize()
+    assert _cos(dx, ref["x"].reshape(rows, width)) > 0.995
+    for k, v in grads.items():
+        assert _cos(v, ref[k]) > 0.99, (k, _cos(v, ref[k]))
+
+
+@pytest.mark.gpu
+def test_training_with_dropout_runs_and_learns():
+    from tests.helpers import build_pair
+    g, cfg, sd, pl, images, labels, tok, tmpl, n_ins, split = _tiny_problem()
+    pair = build_pair("tiny", n_cls=int(g["n_cls"]), shots=3, device=DEV)
+    model = pair.model
+    model.num_ins = n_ins
+    model.prompt_learner.train()
+    tr = model.trainer(lr=2e-3, dropout=0.1, seed=5)
+    assert tr.agg.p_drop == 0.1
+    losses = [tr.step(images.to(DEV), labels.to(DEV), split_point=split) for _ in range(10)]
+    assert all(np.isfinite(losses))
+    assert sum(losses[-3:]) < sum(losses[:3])
     model.prompt_learner.eval()
