@@ -411,6 +411,31 @@ class MM_CLS_OP:
     def parse_batch_train(self, batch):
         return batch["img"].to(self.device), batch["label"].to(self.device)
 
+    def save_model(self, epoch, directory, is_best=False, val_result=None, model_name=""):
+        """dassl/engine/trainer.py:111-160 + dassl/utils/torchtools.py:27-74: `<directory>/prompt_learner/
+        model.pth.tar-<epoch+1>` = {state_dict, epoch, optimizer, scheduler, val_result} (+ the `checkpoint` pointer file
+        and `model-best.pth.tar`), the layout `load_model` and the reference's own loader read."""
+        import shutil
+        save_dir = osp.join(directory, "prompt_learner")
+        os.makedirs(save_dir, exist_ok=True)
+        tr = getattr(self.model, "_trainer", None)
+        optim = None
+        if tr is not None:   # native Adam state in torch.optim.Adam's state_dict layout
+            names = list(tr.params)
+            optim = {"state": {i: {"step": torch.tensor(float(tr.t)), "exp_avg": tr.state[n][0].cpu(),
+                                   "exp_avg_sq": tr.state[n][1].cpu()} for i, n in enumerate(names)},
+                     "param_groups": [{"lr": tr.lr, "betas": tuple(tr.betas), "eps": tr.eps, "weight_decay": tr.wd,
+                                       "amsgrad": False, "params": list(range(len(names)))}]}
+        state = {"state_dict": {k: v.detach().cpu() for k, v in self.model.prompt_learner.state_dict().items()},
+                 "epoch": epoch + 1, "optimizer": optim, "scheduler": None, "val_result": val_result}
+        fpath = osp.join(save_dir, model_name or "model.pth.tar-" + str(epoch + 1))
+        torch.save(state, fpath)
+        with open(osp.join(save_dir, "checkpoint"), "w+") as f:
+            f.write("{}\n".format(osp.basename(fpath)))
+        if is_best:
+            shutil.copy(fpath, osp.join(save_dir, "model-best.pth.tar"))
+        return fpath
+
     def model_inference(self, input, scale_no=None, label=None, eval_set_loader=None):
         return self.model(input, eval_set_loader=eval_set_loader, scale_no=scale_no, label=label)
 

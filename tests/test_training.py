@@ -286,3 +286,31 @@ def test_training_with_dropout_runs_and_learns():
     assert all(np.isfinite(losses))
     assert sum(losses[-3:]) < sum(losses[:3])
     model.prompt_learner.eval()
+
+
+@pytest.mark.gpu
+def test_trainer_shell_step_and_checkpoint_round_trip(tmp_path):
+    """MM_CLS_OP.forward_backward (trainers/...:421-452) + save_model / load_model in the reference's checkpoint
+    layout (dassl/engine/trainer.py:111-160): {state_dict, epoch, optimizer, scheduler, val_result} under
+    <dir>/prompt_learner/model.pth.tar-<epoch>, token_prefix / token_suffix ignored, strict=False."""
+    from tests.helpers import build_pair
+    from ovmr_b200.trainers.mm_classifier_one_prompt import MM_CLS_OP
+    g, cfg, sd, pl, images, labels, tok, tmpl, n_ins, split = _tiny_problem()
+    pair = build_pair("tiny", n_cls=int(g["n_cls"]), shots=3, device=DEV)
+    shell = MM_CLS_OP.__new__(MM_CLS_OP)            # (build_model resolves a checkpoint path through clip.load)
+    shell.cfg, shell.device, shell.model = pair.cfg, torch.device(DEV), pair.model
+    pair.model.num_ins = n_ins
+    out = shell.forward_backward({"img": images, "label": labels})
+    assert np.isfinite(out["loss"])
+    path = shell.save_model(4, str(tmp_path), is_best=True, val_result=12.5)
+    ck = torch.load(path, map_location="cpu")
+    assert set(ck) == {"state_dict", "epoch", "optimizer", "scheduler", "val_result"} and ck["epoch"] == 5
+    assert os.path.exists(tmp_path / "prompt_learner" / "model-best.pth.tar")
+    trained = {k: v.detach().clone() for k, v in pair.model.prompt_learner.state_dict().items()}
+    fresh = build_pair("tiny", n_cls=int(g["n_cls"]), shots=3, device=DEV)
+    shell2 = MM_CLS_OP.__new__(MM_CLS_OP)
+    shell2.cfg, shell2.device, shell2.model = fresh.cfg, torch.device(DEV), fresh.model
+    shell2.load_model(str(tmp_path), epoch=5)
+    for k, v in fresh.model.prompt_learner.state_dict().items():
+        assert torch.equal(v.cpu(), trained[k].cpu()), k
+    pair.model.prompt_learner.eval()
