@@ -156,7 +156,8 @@ class ResidualAttentionBlockWithDropout(nn.Module, _PackedTransformerMixin):
 
     def forward(self, x: torch.Tensor):
         if self.training and self.attn.dropout > 0:
-            raise NotImplementedError("training-mode dropout is outside the eval hot path (SURVEY.md §8f.4)")
+            raise NotImplementedError("module-level forward in training mode with dropout: use CustomCLIP.forward / "
+                                      "ovmr_b200.training (hashed dropout masks, native backward)")
         return self._run(x, _is_causal(self.attn_mask))
 
 
@@ -186,7 +187,8 @@ class TransformerDropout(nn.Module, _PackedTransformerMixin):
 
     def forward(self, x: torch.Tensor):
         if self.training and self.dropout > 0:
-            raise NotImplementedError("training-mode dropout is outside the eval hot path (SURVEY.md §8f.4)")
+            raise NotImplementedError("module-level forward in training mode with dropout: use CustomCLIP.forward / "
+                                      "ovmr_b200.training (hashed dropout masks, native backward)")
         return self._run(x, _is_causal(self.resblocks[0].attn_mask))
 
 

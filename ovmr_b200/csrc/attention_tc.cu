@@ -8,11 +8,12 @@
 //   P = softmax    128 threads, one query row each: tcgen05.ld S, masked max, exp2, row sum,
 //                  P packed to 16-bit and written BACK INTO TMEM over S (tcgen05.st)
 //   O = P V        tcgen05.mma  M=128, N=64, K=Lpad   A = P from TMEM, B = V from smem (MN-major)
-//   out = O / sum  tcgen05.ld O, scale, 128 B per row to global
+//   out = O / sum  tcgen05.ld O, scale, 16-bit rows into a swizzled smem box per warp, one TMA store per box
+//                  (3-D tensor map [seq][row][col]: clipped at the sequence's last row)
 //
 // Warp roles (384 threads): warp 0 TMA producer, warp 1 UMMA issuer, warp 2 TMEM allocator,
-// warps 4-7 / 8-11 two softmax groups that ping-pong over consecutive query tiles (tile t uses
-// TMEM region t&1), so the exp-bound softmax of one tile overlaps the MMAs of the next.
+// warps 4-7 / 8-11 two softmax groups over consecutive query tiles (tile t uses TMEM region t&1), so the softmax
+// of one tile overlaps the MMAs of the next.  The issuing lanes are picked with elect.sync on a converged warp.
 // TMEM map per region (256 columns): S [0,Lpad) fp32; P [0,Lpad/2) packed 16-bit (aliases S, written
 // only after the whole S row has been read twice); O [128,192) fp32 (S columns that are dead by then).
 #include "attention.cuh"
