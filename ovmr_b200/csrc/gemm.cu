@@ -8,8 +8,9 @@
 // (trainers/mm_classifier_one_prompt.py:263-265, 358-360).
 //
 // Two kernels share the same structure (384 threads):
-//   warp 0 / lane 0 : TMA producer   — A / B 16-bit tiles (128-B swizzle) into an mbarrier ring
-//   warp 1 / lane 0 : UMMA issuer    — tcgen05.mma, fp32 accumulators in TMEM, 2 accumulator stages
+//   warp 0          : TMA producer   — A / B 16-bit tiles (128-B swizzle) into an mbarrier ring
+//   warp 1          : UMMA issuer    — tcgen05.mma, fp32 accumulators in TMEM, 2 accumulator stages
+//                     (both warps stay converged; the issuing lane is picked by elect.sync, see common.cuh)
 //   warp 2          : TMEM allocator
 //   warps 4..11     : epilogue       — tcgen05.ld -> fused epilogue -> global
 //  * gemm_tn_kernel<BLOCK_N>   one CTA per SM, 128 x BLOCK_N tiles (cta_group::1)
@@ -27,6 +28,11 @@
 //   EPI_F32_RESID  fp32 out = acc + bias + resid: the residual box (32 rows x 32 cols) is TMA-LOADED into the
 //                  staging buffer one chunk ahead (and L2-prefetched one tile ahead), updated in place by the
 //                  owning threads and TMA-stored.
+//   EPI_F32_RESID_EMIT / EPI_16(_GELU)_LN   the two halves of LayerNorm folding (gemm.cuh): the residual epilogue
+//                  also stores a 16-bit copy of its rows plus per-row slab statistics, the 16-bit epilogue applies
+//                  rstd * (acc - mean * colsum) + bias'.  Parity-tested, off by default (measured slower in situ).
+// All launches carry the programmatic-dependent-launch attribute: the prologue above pdl_wait() overlaps the tail
+// of the previous kernel.  `ep.reverse` walks the tiles last-to-first (alternating sweep direction, api.cu).
 #include "gemm.cuh"
 
 #include "common.cuh"
