@@ -144,3 +144,27 @@ def test_training_branch_oracle_matches_reference_golden():
     for k in g.files:
         if k.startswith("grad:"):
             assert (grads[k[5:]] - torch.from_numpy(g[k])).abs().max() < 1e-5, k
+
+
+def test_coop_fusion_oracle_matches_reference_golden():
+    """trainers/coop_mm_classifier.py (eval branch) restated in the oracle == the executed reference
+    (oracle/gen_golden_coop.py): prompt assembly, read-out rule, F1 fusion weights, fused probabilities."""
+    from ovmr_b200.clip import tokenize
+    g = _load("coop_tiny")
+    n_cls, shots = int(g["n_cls"]), int(g["shots"])
+    cfg = O.CLIP_CONFIGS["tiny"]
+    sd = O.init_clip_state(cfg, seed=0)
+    names = [f"class_{i}" for i in range(n_cls)]
+    tok = tokenize(["X X X X " + n.replace("_", " ") + "." for n in names])
+    sets = O.coop_prompt_sets(sd, torch.from_numpy(g["ctx"]), tok, tokenize("X X X X."), torch.from_numpy(g["visual_tokens"]))
+    feats = O.coop_text_features(sd, sets, tok)
+    assert (torch.stack(feats) - torch.from_numpy(g["features"])).abs().max() < 1e-5
+    scale = sd["logit_scale"].exp()
+    ex = O.synth_images(n_cls * shots, cfg[1], seed=21)
+    ef = O.l2n(O.encode_image(sd, ex)).reshape(n_cls, shots, -1)
+    fw, _, _ = O.fusion_weights(scale, ef, feats[0], feats[1], feats[2], 10.0)
+    assert (fw - torch.from_numpy(g["fusion_weight"])).abs().max() < 1e-6
+    probs = O.classify(scale, O.l2n(O.encode_image(sd, O.synth_images(7, cfg[1], seed=22))),
+                       {"mm_classifier": feats[0], "vision_classifier": feats[1], "text_classifier": feats[2],
+                        "fusion_weight": fw}, "fusion")
+    assert (probs - torch.from_numpy(g["probs"])).abs().max() < 1e-5

@@ -146,8 +146,13 @@ def test_coop_fusion_variant_matches_oracle(tiny, tmp_path):
                                 VISUAL_TOKEN_PATH=str(tmp_path / "visual_tokens.pt"))),
              INPUT=NS(SIZE=(tiny.res, tiny.res)), DATALOADER=NS(TEST=NS(N_INS=shots)))
     names = [f"class_{i}" for i in range(n_cls)]
+    gold = np.load(os.path.join(GOLDEN, "coop_tiny.npz"))      # outputs of the reference's own module on these inputs
+    assert int(gold["n_cls"]) == n_cls and int(gold["shots"]) == shots and int(gold["n_ctx"]) == n_ctx
+    assert np.array_equal(gold["visual_tokens"], vtok.numpy())
     torch.manual_seed(5)
     model = CM.CustomCLIP(cfg, names, tiny.clip).eval()
+    with torch.no_grad():
+        model.prompt_learner.ctx.copy_(torch.from_numpy(gold["ctx"]))
     ctx = model.prompt_learner.ctx.detach().cpu()
     tok = tokenize(["X X X X " + n.replace("_", " ") + "." for n in names])
     tmpl = tokenize("X X X X.")
@@ -158,6 +163,8 @@ def test_coop_fusion_variant_matches_oracle(tiny, tmp_path):
     ref_cls = O.coop_text_features(tiny.sd, sets, tok)
     our_cls = model.classifiers()
     for a, b in zip(our_cls, ref_cls):
+        assert _mincos(a, b) > 0.999
+    for a, b in zip(our_cls, torch.from_numpy(gold["features"])):
         assert _mincos(a, b) > 0.999
     ex = O.synth_images(n_cls * shots, tiny.res, seed=21)
     labels = torch.arange(n_cls).repeat_interleave(shots)
@@ -173,6 +180,8 @@ def test_coop_fusion_variant_matches_oracle(tiny, tmp_path):
                                {"mm_classifier": ref_cls[0], "vision_classifier": ref_cls[1],
                                 "text_classifier": ref_cls[2], "fusion_weight": fw}, "fusion")
         assert (probs.cpu() - ref_probs).abs().max() < 2e-2
+        assert (model.fusion_weight.cpu() - torch.from_numpy(gold["fusion_weight"])).abs().max() < 1e-6
+        assert (probs.cpu() - torch.from_numpy(gold["probs"])).abs().max() < 2e-2
 
 
 def test_text_encoder_and_prompt_learner_api(tiny):
