@@ -168,3 +168,22 @@ def test_coop_fusion_oracle_matches_reference_golden():
                        {"mm_classifier": feats[0], "vision_classifier": feats[1], "text_classifier": feats[2],
                         "fusion_weight": fw}, "fusion")
     assert (probs - torch.from_numpy(g["probs"])).abs().max() < 1e-5
+
+
+def test_zeroshot_oracle_matches_reference_golden():
+    """trainers/zsclip.py (ZeroshotCLIP / ZeroshotCLIP2 build_model + model_inference) restated in the oracle == the
+    executed reference (oracle/gen_golden_zsclip.py)."""
+    from ovmr_b200.clip import tokenize
+    from ovmr_b200.trainers.zsclip import CUSTOM_TEMPLATES, IMAGENET_TEMPLATES_SELECT
+    g = _load("zsclip_tiny")
+    cfg = O.CLIP_CONFIGS["tiny"]
+    sd = O.init_clip_state(cfg, seed=0)
+    names = ["tabby_cat", "golden retriever", "fire truck", "espresso", "x"]
+    img = O.synth_images(6, cfg[1], seed=8)
+    for cls_name, ds in (("ZeroshotCLIP", "ImageNet"), ("ZeroshotCLIP2", "ImageNet"), ("ZeroshotCLIP2", "OxfordPets")):
+        temps = [CUSTOM_TEMPLATES[ds]] if cls_name == "ZeroshotCLIP" else list(IMAGENET_TEMPLATES_SELECT) + (
+            [CUSTOM_TEMPLATES[ds]] if ds != "ImageNet" else [])
+        sets = [torch.cat([tokenize(t.format(n.replace("_", " "))) for n in names]) for t in temps]
+        w = O.template_ensemble_classifier(sd, sets)
+        assert (w - torch.from_numpy(g[f"{cls_name}_{ds}_text_features"])).abs().max() < 1e-5
+        assert (O.zeroshot_logits(sd, img, w) - torch.from_numpy(g[f"{cls_name}_{ds}_logits"])).abs().max() < 1e-4

@@ -102,6 +102,9 @@ def test_zeroshot_clip_baselines_match_oracle(tiny):
         out = zs.model_inference(img.to(DEV))
         assert out.shape == ref_logits.shape
         assert (out.cpu() - ref_logits).abs().max() < 2e-2
+        gold = np.load(os.path.join(GOLDEN, "zsclip_tiny.npz"))   # the reference's own zsclip.py on these inputs
+        assert _mincos(zs.text_features, torch.from_numpy(gold[f"{cls.__name__}_{ds}_text_features"])) > 0.999
+        assert (out.cpu() - torch.from_numpy(gold[f"{cls.__name__}_{ds}_logits"])).abs().max() < 2e-2
         idx, val = zs.predict_topk(img.to(DEV), k=2)
         assert idx.shape == (6, 2)
 
