@@ -134,3 +134,19 @@ def test_plan_batches_partitions_exactly_and_respects_cap():
         for o, z in plan:
             assert o == off
             off += z
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (CPU port of the reference on the host cores): one JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--cpu-sample-classes", "1", "--shots", "2"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "img/s" and line["value"] > 0 and line["higher_is_better"] is True
+    for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
