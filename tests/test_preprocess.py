@@ -40,6 +40,19 @@ def test_host_coefficients_match_oracle(in_size, out_size):
     assert np.array_equal(b, rb) and np.array_equal(k, rk)
 
 
+def test_host_bilinear_coefficients_reproduce_pillow():
+    """filter = 2 (bilinear, Dassl's default INPUT.INTERPOLATION): the product's host coefficient tables drive the numpy
+    two-pass resampler to Pillow's exact output."""
+    Image = pytest.importorskip("PIL.Image")
+    from ovmr_b200.preprocess import BILINEAR, resample_coeffs
+    for i, (h, w, oh, ow) in enumerate([(123, 77, 50, 31), (31, 45, 97, 140), (200, 150, 64, 48)]):
+        img = P.synth_rgb(h, w, 200 + i)
+        ref = np.asarray(Image.fromarray(img, mode="RGB").resize((ow, oh), resample=Image.BILINEAR))
+        xb, xk = resample_coeffs(w, ow, BILINEAR)
+        yb, yk = resample_coeffs(h, oh, BILINEAR)
+        assert np.array_equal(P.resample_two_pass(img, xb, xk, yb, yk), ref)
+
+
 def test_resize_geometry_matches_torchvision_rules():
     from ovmr_b200.preprocess import center_crop_origin, resized_size
     assert resized_size(256, 341, 224) == (224, 298)
