@@ -147,6 +147,11 @@ int ovmr_layernorm(const float* x, long long ldx, int rows, int width, const int
 /* nn.MultiheadAttention core (clip/model.py:184-189): qkv bf16 [n_seq*L, 3D] -> out bf16 [n_seq*L, D]. */
 int ovmr_attention(const void* qkv, void* out, int n_seq, int seq_len, int width, int heads, int causal,
                    int fp16, void* stream);
+/* Same, with the kernel chosen by the caller (A/B measurements and parity tests of every implementation):
+ * impl 0 = shape dispatch (what ovmr_attention does), 1 = streaming mma.sync kernel, 2 = single-block tcgen05
+ * kernel (seq_len <= 256), 3 = key-blocked tcgen05 kernel (any seq_len). */
+int ovmr_attention_impl(const void* qkv, void* out, int n_seq, int seq_len, int width, int heads, int causal,
+                        int fp16, int impl, void* stream);
 
 /* conv1 input as GEMM operand (clip/model.py:412-414): fp32 NCHW -> bf16 [batch*G*G, ldo]. */
 int ovmr_patchify(const float* images, void* out_16bit, int batch, int resolution, int patch, int ldo, int fp16,

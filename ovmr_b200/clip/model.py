@@ -55,15 +55,26 @@ class QuickGELU(nn.Module):
 class _PackedTransformerMixin:
     """Lazy packing of a Transformer-like module into an ovmr_transformer descriptor."""
 
+    def _param_signature(self):
+        """(storage pointer, autograd version) of every parameter: changes whenever an optimiser step, load_state_dict
+        or any other in-place write touches the fp32 masters."""
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
     def _packed(self, device):
+        """16-bit operand copies of the current parameters.  The copies are rebuilt whenever the parameters have been
+        written since they were packed (torch.optim steps, load_state_dict), so evaluation never runs on stale weights."""
         p = getattr(self, "_ovmr_packed", None)
-        if p is None or p.device != device:
+        sig = self._param_signature()
+        if p is None or p.device != device or getattr(self, "_ovmr_sig", None) != sig:
             p = E.PackedTransformer(self, device, precision().text_fp16)
             object.__setattr__(self, "_ovmr_packed", p)
-            object.__setattr__(self, "_ovmr_ws", E.Workspace(device))
+            object.__setattr__(self, "_ovmr_sig", sig)
+            if getattr(self, "_ovmr_ws", None) is None or self._ovmr_ws.device != device:
+                object.__setattr__(self, "_ovmr_ws", E.Workspace(device))
         return p
 
     def repack(self):
+        """Force a re-pack (needed only after writes that bypass torch's version counter, e.g. the native Adam kernel)."""
         object.__setattr__(self, "_ovmr_packed", None)
 
     def _run(self, x: torch.Tensor, causal: bool):

@@ -331,6 +331,12 @@ int ovmr_attention(const void* qkv, void* out, int n_seq, int seq_len, int width
   return ovmr::attention(qkv, out, n_seq, seq_len, width, heads, causal, fp16 != 0, S(stream));
 }
 
+int ovmr_attention_impl(const void* qkv, void* out, int n_seq, int seq_len, int width, int heads, int causal, int fp16,
+                        int impl, void* stream) {
+  OVMR_REQUIRE(impl >= 0 && impl <= 3, "attention_impl: impl=%d", impl);
+  return ovmr::attention(qkv, out, n_seq, seq_len, width, heads, causal, fp16 != 0, S(stream), 0, impl);
+}
+
 int ovmr_patchify(const float* images, void* out_16bit, int batch, int resolution, int patch, int ldo, int fp16,
                   void* stream) {
   return ovmr::patchify(images, out_16bit, batch, resolution, patch, ldo, fp16 != 0, S(stream));

@@ -217,16 +217,19 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 }  // namespace
 
 int attention(const void* qkv, void* out, int n_seq, int L, int D, int heads, int causal, int fp16, cudaStream_t stream,
-              int reverse) {
+              int reverse, int force_impl) {
   OVMR_REQUIRE(n_seq > 0 && L > 0 && heads > 0 && D == heads * HD, "attention: need D == heads*64 (D=%d heads=%d L=%d)", D,
                heads, L);
-  // shape specialisation: the vision towers' sequence lengths run on the tcgen05 kernel; short sequences (text,
-  // aggregator) and L > 256 (ViT-L/14) on the streaming mma.sync kernel below.  OVMR_ATTN_IMPL=legacy|tc overrides.
-  static const int impl = [] {
+  // shape specialisation: sequences longer than 64 tokens (the vision towers: 197 / 257 / 577) run on the key-blocked
+  // tcgen05 kernel (attention_kv.cu); short sequences (text at its effective length, aggregator) on the streaming
+  // mma.sync kernel below.  OVMR_ATTN_IMPL=legacy|tc|kv overrides (tc = the single-block tcgen05 kernel, L <= 256).
+  static const int env_impl = [] {
     const char* e = getenv("OVMR_ATTN_IMPL");
-    return e == nullptr ? 0 : (!strcmp(e, "legacy") ? 1 : (!strcmp(e, "tc") ? 2 : 0));
+    return e == nullptr ? 0 : (!strcmp(e, "legacy") ? 1 : (!strcmp(e, "tc") ? 2 : (!strcmp(e, "kv") ? 3 : 0)));
   }();
-  if (L <= 256 && (impl == 2 || (impl == 0 && L > 64))) return attention_tc(qkv, out, n_seq, L, D, heads, causal, fp16, stream, reverse);
+  const int impl = force_impl ? force_impl : env_impl;
+  if (impl == 3 || (impl == 0 && L > 64)) return attention_kv(qkv, out, n_seq, L, D, heads, causal, fp16, stream, reverse);
+  if (impl == 2 && L <= 256) return attention_tc(qkv, out, n_seq, L, D, heads, causal, fp16, stream, reverse);
   OVMR_REQUIRE(n_seq <= 65535 && heads <= 65535, "attention: grid limits (n_seq=%d)", n_seq);
   const int nkb = (L + KB - 1) / KB;
   const size_t smem = (static_cast<size_t>(2) * nkb * KB + QT) * PITCH * 2;

@@ -80,8 +80,17 @@ class TowerState:
         self.ws = E.Workspace(device)
         self.repack()
 
+    def _param_signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.module.parameters())
+
+    def sync(self):
+        """Re-pack when the fp32 masters were written since the last pack (external torch optimiser, load_state_dict)."""
+        if self.trainable and self._sig != self._param_signature():
+            self.repack()
+
     def repack(self):
         dev = self.device
+        self._sig = self._param_signature()
         f32 = lambda t: t.detach().to(device=dev, dtype=F32).contiguous()
         b16 = lambda t: t.detach().to(device=dev, dtype=F32).to(BF16).contiguous()
         self.layers = []
@@ -300,6 +309,7 @@ class GeneratorTrainer:
     def loss_and_grads(self, image: torch.Tensor, label: torch.Tensor, split_point: Optional[int] = None):
         m, dev, lib, st = self.m, self.device, L.lib(), L.stream()
         pl = m.prompt_learner
+        self.agg.sync()   # the loss must be evaluated at the CURRENT aggregator weights (torch.optim steps between calls)
         n_ins = m.num_ins
         num_cls = image.shape[0] // n_ins
         if split_point is None:      # trainers/...:301

@@ -139,6 +139,65 @@ def test_attention(n_seq, Lq, heads, causal, fp16):
     assert err < (4e-3 if fp16 else 2e-2), err
 
 
+def _attention_ref(qkv, n_seq, Lq, heads, causal):
+    D = heads * 64
+    q, k, v = (t.view(n_seq, Lq, heads, 64).transpose(1, 2) for t in qkv.split(D, dim=-1))
+    s = (q @ k.transpose(-1, -2)) / 8.0
+    if causal:
+        s = s + torch.full((Lq, Lq), float("-inf")).triu_(1)
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(n_seq * Lq, D)
+
+
+# impl 1 = streaming mma.sync kernel, 2 = single-block tcgen05 kernel (L <= 256), 3 = key-blocked tcgen05 kernel
+@pytest.mark.parametrize("n_seq,Lq,heads,causal", [(3, 197, 12, 0), (5, 77, 8, 1), (2, 16, 2, 0), (2, 96, 2, 0), (2, 97, 2, 1),
+                                                   (2, 112, 2, 0), (3, 113, 2, 0), (2, 208, 2, 1), (2, 209, 2, 0),
+                                                   (2, 256, 2, 0), (3, 257, 16, 0), (2, 300, 2, 1), (2, 577, 16, 0),
+                                                   (1, 577, 2, 1), (170, 197, 2, 0), (7, 50, 2, 0)])
+@pytest.mark.parametrize("fp16", [0, 1])
+@pytest.mark.parametrize("impl", [1, 2, 3])
+def test_attention_every_implementation(n_seq, Lq, heads, causal, fp16, impl):
+    if impl == 2 and Lq > 256:
+        pytest.skip("single-block tcgen05 kernel: L <= 256")
+    L, lib = _lib()
+    t16 = torch.float16 if fp16 else torch.bfloat16
+    D = heads * 64
+    g = torch.Generator().manual_seed(n_seq * 1000 + Lq)
+    qkv = _bf16r(torch.randn(n_seq * Lq, 3 * D, generator=g))
+    ref = _attention_ref(qkv, n_seq, Lq, heads, causal)
+    QKV = qkv.to(DEV).to(t16)
+    out = torch.zeros(n_seq * Lq, D, dtype=t16, device=DEV)
+    L.check(lib.ovmr_attention_impl(QKV.data_ptr(), out.data_ptr(), n_seq, Lq, D, heads, causal, fp16, impl, L.stream()))
+    torch.cuda.synchronize()
+    err = (out.cpu().float() - ref).abs().max().item()
+    assert err < (4e-3 if fp16 else 2e-2), err
+
+
+@pytest.mark.parametrize("Lq,causal", [(197, 0), (257, 0), (577, 0), (300, 1)])
+def test_attention_kv_lazy_rescale_path(Lq, causal):
+    """Logits that GROW along the key axis (later key blocks beat the reference maximum of block 0 by far more than
+    2^8) force the key-blocked kernel through its O-accumulator rescale; the result must still be softmax(QK^T/8)V."""
+    L, lib = _lib()
+    n_seq, heads = 3, 4
+    D = heads * 64
+    g = torch.Generator().manual_seed(Lq)
+    qkv = torch.randn(n_seq * Lq, 3 * D, generator=g)
+    ramp = torch.linspace(0.5, 4.0, Lq).repeat(n_seq)[:, None]      # key norm grows with the position
+    qkv[:, D:2 * D] *= ramp
+    qkv[:, :D] *= 2.0
+    qkv = _bf16r(qkv)
+    ref = _attention_ref(qkv, n_seq, Lq, heads, causal)
+    QKV = qkv.to(DEV).bfloat16()
+    outs = []
+    for impl in (1, 3):
+        out = torch.zeros(n_seq * Lq, D, dtype=torch.bfloat16, device=DEV)
+        L.check(lib.ovmr_attention_impl(QKV.data_ptr(), out.data_ptr(), n_seq, Lq, D, heads, causal, 0, impl, L.stream()))
+        torch.cuda.synchronize()
+        outs.append(out.cpu().float())
+    assert torch.isfinite(outs[1]).all()
+    assert (outs[1] - ref).abs().max() < 4e-2, (outs[1] - ref).abs().max()
+    assert (outs[0] - ref).abs().max() < 4e-2
+
+
 @pytest.mark.parametrize("B,R,P", [(3, 64, 16), (2, 224, 16), (2, 224, 14), (1, 224, 32)])
 def test_patchify(B, R, P):
     L, lib = _lib()

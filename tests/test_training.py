@@ -205,6 +205,61 @@ def test_native_training_step_matches_oracle_autograd():
 
 
 @pytest.mark.gpu
+def test_external_torch_optimizer_sees_fresh_weights_every_step():
+    """The reference's own loop — `loss = model(image, label); loss.backward(); optim.step()` with a torch optimiser —
+    must evaluate every loss at the CURRENT aggregator weights: the 16-bit operand copies of the training towers and
+    of the eval path are re-packed whenever the fp32 masters were written.  Two torch.optim.Adam steps through
+    autograd must match two native `GeneratorTrainer.step` calls from the same start (same split point, no dropout)."""
+    import copy
+    from tests.helpers import build_pair
+    g, cfg, sd, pl, images, labels, tok, tmpl, n_ins, split = _tiny_problem()
+    n_cls = int(g["n_cls"])
+    img, lab = images.to(DEV), labels.to(DEV)
+
+    def fresh():
+        pair = build_pair("tiny", n_cls=n_cls, shots=3, device=DEV)
+        pair.model.num_ins = n_ins
+        pair.model.prompt_learner.train()
+        return pair.model
+
+    # (a) native steps
+    ma = fresh()
+    tra = ma.trainer(lr=1e-3, dropout=0.0)
+    la = [tra.step(img, lab, split_point=split, lr=1e-3) for _ in range(3)]
+    # (b) torch.optim.Adam over autograd, the trainer only supplies loss + gradients
+    mb = fresh()
+    trb = mb.trainer(lr=1e-3, dropout=0.0)
+    from ovmr_b200.training import _NativeLoss
+    names = list(trb.params)
+    opt = torch.optim.Adam([trb.params[n] for n in names], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    lb = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = _NativeLoss.apply(trb, img, lab, split, names, *[trb.params[n] for n in names])
+        loss.backward()
+        opt.step()
+        lb.append(float(loss))
+    torch.cuda.synchronize()
+    assert lb[1] != lb[0] and lb[2] != lb[1]          # the loss moves: it is evaluated at the updated weights
+    for a, b in zip(la, lb):
+        assert abs(a - b) < 2e-3, (la, lb)
+    # Adam normalises every element's step to ~lr, so elements whose true gradient is zero (e.g. the key bias: softmax is
+    # shift invariant) move by +-lr on reduction-order noise: compare the update DIRECTION of the whole parameter vector
+    p0 = dict(fresh().prompt_learner.named_parameters())
+    ua = torch.cat([(pa - p0[k]).flatten() for k, pa in ma.prompt_learner.named_parameters()])
+    ub = torch.cat([(pb - p0[k]).flatten() for k, pb in mb.prompt_learner.named_parameters()])
+    assert _cos(ua, ub) > 0.98, _cos(ua, ub)
+    # the eval path of (b) also runs on the updated aggregator: visual tokens agree with model (a)'s
+    ma.prompt_learner.eval(), mb.prompt_learner.eval()
+    feats = torch.nn.functional.normalize(torch.randn(n_cls, 3, cfg[0], device=DEV), dim=-1)
+    va, vb = ma.prompt_learner.visual_tokens(feats), mb.prompt_learner.visual_tokens(feats)
+    assert _cos(va.cpu(), vb.cpu()) > 0.9999
+    # and differs from the initial aggregator's (a stale pack would reproduce these)
+    v0 = fresh().prompt_learner.eval().visual_tokens(feats)
+    assert (vb - v0).abs().max() > 1e-4
+
+
+@pytest.mark.gpu
 def test_dropout_masks_and_training_block_with_dropout_match_autograd():
     """Training-mode dropout (hashed masks): mask statistics and determinism; then one aggregator block in training
     mode — forward output and every gradient — against torch.autograd on the same block with the SAME masks (read
