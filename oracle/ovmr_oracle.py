@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY — CPU fp32 restatement of OVMR's hot path (the parity oracle).
+"""TEST INFRASTRUCTURE ONLY — fp32 restatement of OVMR's hot path (the parity oracle): plain torch ops, run on the CPU
+by the tests and, unchanged, in fp32 (TF32 off) on the GPU by bench.py's parity block at the benchmarked configurations.
 
 Nothing under `ovmr_b200/` imports this module.  Only `tests/`, `__graft_entry__.smoke()` and
 `bench.py`'s cpu_baseline / `--impl reference` legs may use it, and only as the checker / the
@@ -216,7 +217,7 @@ def attention(x: Tensor, sd: State, prefix: str, heads: int, causal: bool) -> Te
     v = v.view(n, l, heads, hd).transpose(1, 2)
     s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
     if causal:
-        s = s + torch.full((l, l), float("-inf")).triu_(1)
+        s = s + torch.full((l, l), float("-inf"), device=s.device).triu_(1)
     p = torch.softmax(s, dim=-1)
     o = (p @ v).transpose(1, 2).reshape(n, l, d)
     return o @ sd[prefix + "attn.out_proj.weight"].t() + sd[prefix + "attn.out_proj.bias"]
@@ -290,7 +291,7 @@ def text_transformer_readout(sd: State, x: Tensor, idx: Tensor, heads: int) -> T
     x = x.float() + sd["positional_embedding"][: x.shape[1]]
     x = transformer(x, sd, "transformer.", layers, heads, causal=True)
     x = layer_norm(x, sd["ln_final.weight"], sd["ln_final.bias"])
-    x = x[torch.arange(x.shape[0]), idx.long()]
+    x = x[torch.arange(x.shape[0], device=x.device), idx.long()]
     return x @ sd["text_projection"]
 
 
@@ -408,7 +409,7 @@ def multiclass_f1(pred: Tensor, target: Tensor, num_classes: int) -> Tensor:
     F1_c = 2 p r / (p + r), p = tp/num_pred, r = tp/num_label, NaN -> 0."""
     # fp32 like torcheval (counts are small integers, exact in fp32; the divisions are IEEE fp32)
     one = torch.ones_like(target, dtype=torch.float32)
-    z = lambda: torch.zeros(num_classes, dtype=torch.float32)
+    z = lambda: torch.zeros(num_classes, dtype=torch.float32, device=target.device)
     n_lab = z().scatter_add_(0, target.long(), one)
     n_pred = z().scatter_add_(0, pred.long(), one)
     hit = pred.long() == target.long()
@@ -422,7 +423,7 @@ def fusion_weights(logit_scale: Tensor, eval_feats: Tensor, mm: Tensor, v: Tenso
     """Tail of forward_prompt (trainers/...:261-274): self-classify the C*S exemplars with each
     classifier, per-class F1, softmax(tau * [F1_mm, F1_v, F1_t])."""
     c, s, e = eval_feats.shape
-    labels = torch.arange(c).reshape(-1, 1).repeat(1, s).flatten()
+    labels = torch.arange(c, device=eval_feats.device).reshape(-1, 1).repeat(1, s).flatten()
     flat = eval_feats.reshape(c * s, e)
     f1s, preds = [], []
     for w in (mm, v, t):
@@ -441,15 +442,18 @@ def forward_prompt(sd: State, pl: State, tokenized_prompts: Tensor, visual_templ
     c = tokenized_prompts.shape[0]
     e = sd["visual.proj"].shape[1]
     n_ctx = pl["cls_token"].shape[0]
-    prompt_tokens = sd["token_embedding.weight"][tokenized_prompts.long()]
-    visual_prompt_temp = sd["token_embedding.weight"][visual_template_tokens.long()]
+    prompt_tokens = sd["token_embedding.weight"][tokenized_prompts.long().to(sd["token_embedding.weight"].device)]
+    visual_prompt_temp = sd["token_embedding.weight"][visual_template_tokens.long().to(sd["token_embedding.weight"].device)]
     logit_scale = sd["logit_scale"].exp()
-    mm_cls = torch.zeros(c, e)
-    v_cls = torch.zeros(c, e)
-    vtoks = torch.zeros(c, n_ctx, e)
-    eval_feats = torch.zeros(c, shots, e)
-    seen = torch.zeros(c, dtype=torch.bool)
+    dev = sd["visual.proj"].device     # (CPU in the tests; bench.py's parity block runs the same code in fp32 on the GPU)
+    tokenized_prompts = tokenized_prompts.to(dev)
+    mm_cls = torch.zeros(c, e, device=dev)
+    v_cls = torch.zeros(c, e, device=dev)
+    vtoks = torch.zeros(c, n_ctx, e, device=dev)
+    eval_feats = torch.zeros(c, shots, e, device=dev)
+    seen = torch.zeros(c, dtype=torch.bool, device=dev)
     for images, labels in exemplar_batches:
+        images, labels = images.to(dev), labels.to(dev)
         cb = images.shape[0] // shots
         ex_label = labels.reshape(cb, shots)[:, 0]
         feats = l2n(encode_image(sd, images)).reshape(cb, shots, -1)

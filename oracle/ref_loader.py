@@ -21,7 +21,21 @@ import types
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("OVMR_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference_root() -> str:
+    """/root/reference (build container) or, where that does not exist (the GPU box), oracle/_ref: a git-ignored copy
+    of the reference's clip/, trainers/ and Dassl.pytorch/dassl/ packages made by oracle/build_ref.py at build() time.
+    The copy is never committed and nothing in the product reads it."""
+    env = os.environ.get("OVMR_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference", os.path.join(_HERE, "_ref")]:
+        if cand and os.path.isfile(os.path.join(cand, "clip", "model.py")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
@@ -106,14 +120,14 @@ def load_reference():
     return _loaded
 
 
-def make_cfg(n_ctx=2, shots=4, out_dir="/tmp", eval_mode="fusion", tau=10, batch=64, n_ins=8):
-    return CN(TRAINER=CN(COCOOP=CN(N_CTX=n_ctx, PREC="fp32")), INPUT=CN(SIZE=(224, 224)),
+def make_cfg(n_ctx=2, shots=4, out_dir="/tmp", eval_mode="fusion", tau=10, batch=64, n_ins=8, image_size=224):
+    return CN(TRAINER=CN(COCOOP=CN(N_CTX=n_ctx, PREC="fp32")), INPUT=CN(SIZE=(image_size, image_size)),
               DATALOADER=CN(TRAIN_X=CN(BATCH_SIZE=batch, N_INS=n_ins), K_TRANSFORMS=1),
               DATASET=CN(NUM_SHOTS=shots), EVAL_MODE=eval_mode, EVAL_TAU=tau, OUTPUT_DIR=out_dir)
 
 
 def build_reference_model(clip_args, classnames, n_ctx, shots, out_dir, seed_clip=0, seed_agg=1,
-                          eval_mode="fusion", tau=10, round_bf16=True):
+                          eval_mode="fusion", tau=10, round_bf16=True, image_size=224):
     """Reference CLIP(...) under manual_seed(seed_clip), CustomCLIP(...) under manual_seed(seed_agg),
     every parameter rounded once to a bf16-representable fp32 value (so that the bf16 CUDA path and
     the fp32 reference share bit-identical weights)."""
@@ -124,7 +138,7 @@ def build_reference_model(clip_args, classnames, n_ctx, shots, out_dir, seed_cli
         with torch.no_grad():
             for p in clip_model.parameters():
                 p.copy_(p.bfloat16().float())
-    cfg = make_cfg(n_ctx=n_ctx, shots=shots, out_dir=out_dir, eval_mode=eval_mode, tau=tau)
+    cfg = make_cfg(n_ctx=n_ctx, shots=shots, out_dir=out_dir, eval_mode=eval_mode, tau=tau, image_size=image_size)
     torch.manual_seed(seed_agg)
     import contextlib
     import io

@@ -65,6 +65,28 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// 2^x on the FMA pipe (Cody-Waite range reduction + degree-3 minimax polynomial on [-0.5, 0.5], max relative error
+// 7.5e-5: far below the 2^-9 rounding of P to 16 bits).  The MUFU serves 4 lanes per clock and sub-partition — one ex2 per
+// 8 cycles and warp — and is the busiest unit of the softmax; a compile-time fraction of the exponentials (OVMR_ATTN_POLY:
+// every n-th element of a row, 0 = none) can be evaluated here instead so that both pipes work in parallel.
+// MEASURED on B200 (profiles/r02_attention_notes.md): slower, not faster, in this kernel — the emulation costs ~9 issue
+// slots per element (3 of them on the half-rate ALU pipe) against 8 MUFU cycles, and the tile time went from 6.3k to
+// 7.1k cycles at every fraction tried (1/2, 1/3, 1/4) — so it is OFF by default and kept only as a build-time experiment.
+#ifndef OVMR_ATTN_POLY
+#define OVMR_ATTN_POLY 0
+#endif
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;          // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float f = x - (t - 12582912.0f);     // x - round(x) in [-0.5, 0.5]
+  float q = fmaf(f, 0.0551716685f, 0.242611125f);
+  q = fmaf(q, f, 0.693260968f);
+  q = fmaf(q, f, 0.999928057f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));   // q * 2^round(x)
+}
+__host__ __device__ constexpr bool on_fma_pipe(int e) {
+  return OVMR_ATTN_POLY > 0 && e % (OVMR_ATTN_POLY > 0 ? OVMR_ATTN_POLY : 1) == (OVMR_ATTN_POLY > 0 ? OVMR_ATTN_POLY : 1) - 1;
+}
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
@@ -184,8 +206,11 @@ __device__ __forceinline__ RowState softmax_block(uint32_t scol, int key0, int n
       uint32_t pk[8];
 #pragma unroll
       for (int e = 0; e < 16; e += 2) {
-        float p0 = ex2f(fmaf(__uint_as_float(s[16 * c + e]), scale_log2e, -m_ref));
-        float p1 = ex2f(fmaf(__uint_as_float(s[16 * c + e + 1]), scale_log2e, -m_ref));
+        // (e is a compile-time constant after unrolling: the pipe is chosen per element position)
+        const float x0 = fmaf(__uint_as_float(s[16 * c + e]), scale_log2e, -m_ref);
+        const float x1 = fmaf(__uint_as_float(s[16 * c + e + 1]), scale_log2e, -m_ref);
+        float p0 = on_fma_pipe(e) ? ex2_poly(x0) : ex2f(x0);
+        float p1 = on_fma_pipe(e + 1) ? ex2_poly(x1) : ex2f(x1);
         if (masked) {
           p0 = (key0 + 16 * c + e <= kmax) ? p0 : 0.f;
           p1 = (key0 + 16 * c + e + 1 <= kmax) ? p1 : 0.f;

@@ -92,13 +92,23 @@ fusion_softmax_topk_kernel(const float* __restrict__ logits, long long ld, int s
   }
   __syncthreads();
   for (int j = 0; j < k; ++j) {
+    // The sentinel never wins against a finite probability.  A row of NaN probabilities (zero-norm feature, fp16
+    // overflow upstream) compares false everywhere: the reference's torch.topk then returns NaN values; here the index
+    // falls back to the first column not yet taken, so that nothing downstream (srow, F1 histograms) is indexed out of range.
     MaxIdx m{-FLT_MAX, 0x7fffffff};
     for (int c = threadIdx.x; c < C; c += blockDim.x) m = better(m, MaxIdx{srow[c], c});
     m = block_argmax(m, red_mi);
     if (threadIdx.x == 0) {
-      top_idx[q * k + j] = m.i;
-      top_val[q * k + j] = m.v;
-      srow[m.i] = -FLT_MAX;  // exclude from the next round
+      int idx = m.i;
+      float val = m.v;
+      if (idx < 0 || idx >= C) {   // no comparable entry left in this row
+        idx = 0;
+        while (idx < C - 1 && srow[idx] == -FLT_MAX) ++idx;
+        val = srow[idx];
+      }
+      top_idx[q * k + j] = idx;
+      top_val[q * k + j] = val;
+      srow[idx] = -FLT_MAX;  // exclude from the next round
     }
     __syncthreads();
   }
@@ -116,7 +126,8 @@ argmax_segments_kernel(const float* __restrict__ logits, long long rows, long lo
   MaxIdx m{-FLT_MAX, 0x7fffffff};
   for (int c = lane; c < C; c += 32) m = better(m, MaxIdx{ls[c], c});
   m = warp_argmax(m);
-  if (lane == 0) pred[r * nseg + s] = m.i;
+  // an all-NaN row has no comparable entry: class 0 (torch.argmax's NaN handling differs, but the index stays in range)
+  if (lane == 0) pred[r * nseg + s] = (m.i >= 0 && m.i < C) ? m.i : 0;
 }
 
 // counts layout: tp[C*nseg] | npred[C*nseg] | nlab[C]   (int32, zeroed by the caller)
@@ -127,12 +138,16 @@ __global__ void f1_counts_kernel(const int* __restrict__ pred, const int* __rest
   int* nlab = counts + 2LL * C * nseg;
   for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < rows;
        r += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // labels and predictions outside [0, C) are not counted (the host wrapper rejects such labels up front; this
+    // keeps a corrupt prediction from scattering outside the histograms)
     const int y = labels[r];
-    atomicAdd(nlab + y, 1);
+    const bool y_ok = y >= 0 && y < C;
+    if (y_ok) atomicAdd(nlab + y, 1);
     for (int s = 0; s < nseg; ++s) {
       const int p = pred[r * nseg + s];
+      if (p < 0 || p >= C) continue;
       atomicAdd(npred + static_cast<long long>(p) * nseg + s, 1);
-      if (p == y) atomicAdd(tp + static_cast<long long>(y) * nseg + s, 1);
+      if (y_ok && p == y) atomicAdd(tp + static_cast<long long>(y) * nseg + s, 1);
     }
   }
 }

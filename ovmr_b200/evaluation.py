@@ -31,6 +31,7 @@ class Classification:
         # [tp (C) | num_pred (C) | num_label (C)] for top-1 predictions, + scalar top-k match counter
         self._counts = torch.zeros(3 * c, dtype=torch.int32, device=self.device)
         self._correct = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._bad_labels = torch.zeros(1, dtype=torch.int64, device=self.device)   # ground-truth labels outside [0, C)
         self._total = 0
 
     def process(self, mo: torch.Tensor, gt: torch.Tensor, topk: int = 1):
@@ -43,6 +44,8 @@ class Classification:
         else:
             pred = mo.to(self.device).topk(k=topk, dim=-1)[1]
         self._correct += (pred == gt32.unsqueeze(1)).any(dim=1).sum()
+        # counted on the device (no per-batch sync); the histogram kernel skips such rows and evaluate() raises
+        self._bad_labels += ((gt32 < 0) | (gt32 >= self.num_classes)).sum()
         self._total += int(gt.shape[0])
         top1 = pred[:, 0].to(torch.int32).contiguous()
         L.check(lib.ovmr_f1_counts(top1.data_ptr(), gt32.data_ptr(), top1.shape[0], 1, self.num_classes,
@@ -50,6 +53,9 @@ class Classification:
 
     def evaluate(self):
         c = self.num_classes
+        bad = int(self._bad_labels.item())
+        if bad:
+            raise ValueError(f"Classification: {bad} ground-truth labels outside [0, {c})")
         cnt = self._counts.cpu().to(torch.float64)
         tp, n_pred, n_lab = cnt[:c], cnt[c:2 * c], cnt[2 * c:]
         correct = int(self._correct.item())

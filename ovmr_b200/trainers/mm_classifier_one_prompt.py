@@ -55,7 +55,11 @@ class TextEncoder(nn.Module):
 class PromptLearner(nn.Module):
     """trainers/...:94-176 — prompt buffers, zero-shot text classifier, aggregator + cls_token."""
 
-    def __init__(self, cfg, classnames, clip_model):
+    def __init__(self, cfg, classnames, clip_model, shard=None):
+        """shard (ovmr_b200.dist.Shard, optional): this rank generates classifiers only for classes [shard.lo, shard.hi)
+        and keeps only their rows of `prompt_tokens` (the [C, 77, W] buffer is the one per-class tensor of size that
+        matters: 3.4 GB in fp32 at 21,841 classes); row r of the buffer then belongs to class shard.lo + r
+        (`prompt_row0`).  The zero-shot text classifier and the tokenised prompts stay complete on every rank."""
         super().__init__()
         n_cls = len(classnames)
         self.cfg = cfg
@@ -85,7 +89,9 @@ class PromptLearner(nn.Module):
             # template axis, F.normalize.  Batched over classes; the reference's C<5000 guard is lifted.
             feats = text.encode_tokens(tokenized_prompts, normalize=False)
             self.zero_shot_classifier = E.segmented_mean(feats.view(n_cls, 1, -1), normalize=True)
-            self.prompt_tokens = text.embed(tokenized_prompts).type(dtype)                    # [C, 77, W]
+            lo, hi = (shard.lo, shard.hi) if shard is not None else (0, n_cls)
+            self.prompt_row0 = lo
+            self.prompt_tokens = text.embed(tokenized_prompts[lo:hi]).type(dtype)             # [C (or C/G), 77, W]
             self.visual_prompt_temp = text.embed(visual_template_tokenized_prompts).type(dtype)  # [1, 77, W]
         self.n_cls = n_cls
         self.n_ctx = n_ctx
@@ -132,7 +138,7 @@ class PromptLearner(nn.Module):
     def forward(self, exemplar_img_feats, label, ori_text_len):
         """trainers/...:159-176 — returns ([mm_prompts], mm_lens, [v_prompts], v_lens, visual tokens)."""
         num_class = exemplar_img_feats.shape[0]
-        prompts = self.prompt_tokens[label]
+        prompts = self.prompt_tokens[label - self.prompt_row0]
         mm_lens = ori_text_len + self.n_ctx
         v_lens = torch.ones_like(ori_text_len, dtype=torch.int32) + self.n_ctx
         agg_img_token_ = self.visual_tokens(exemplar_img_feats).type(exemplar_img_feats.dtype)
@@ -146,10 +152,10 @@ class CustomCLIP(nn.Module):
 
     GEN_GROUP = 128   # classes per aggregator / text-tower pass in forward_prompt
 
-    def __init__(self, cfg, classnames, clip_model):
+    def __init__(self, cfg, classnames, clip_model, shard=None):
         super().__init__()
         self.cfg = cfg
-        self.prompt_learner = PromptLearner(cfg, classnames, clip_model)
+        self.prompt_learner = PromptLearner(cfg, classnames, clip_model, shard=shard)
         self.tokenized_prompts = self.prompt_learner.tokenized_prompts
         self.image_encoder = clip_model.visual
         self.text_encoder = TextEncoder(clip_model)
@@ -203,7 +209,8 @@ class CustomCLIP(nn.Module):
         # the longest class prompt
         mm_idx = pl.eot_index_dev[exemplar_label.long()] + pl.n_ctx
         v_idx = torch.full_like(mm_idx, 1 + pl.n_ctx)
-        mm = text.encode_spliced(pl.prompt_tokens, exemplar_label, vtok, mm_idx, pl.max_eot + pl.n_ctx, normalize=True)
+        mm = text.encode_spliced(pl.prompt_tokens, exemplar_label - pl.prompt_row0, vtok, mm_idx, pl.max_eot + pl.n_ctx,
+                                 normalize=True)
         v = text.encode_spliced(pl.visual_prompt_temp, None, vtok, v_idx, 1 + pl.n_ctx, normalize=True)
         # mean over the (length-1) prompt list + second normalisation (trainers/...:210-211)
         mm = E.segmented_mean(mm.unsqueeze(1), normalize=True)

@@ -338,7 +338,7 @@ class GeneratorTrainer:
         loss = torch.zeros(1, dtype=F32, device=dev)
         mm_idx = pl.eot_index_dev[ex_label.long()] + n_ctx
         v_idx = torch.full_like(mm_idx, 1 + n_ctx)
-        dvtok = self._prompt_set(pl.prompt_tokens, ex_label, vtok, mm_idx, pl.max_eot + n_ctx, f_img, train_labels, scale, loss)
+        dvtok = self._prompt_set(pl.prompt_tokens, ex_label - pl.prompt_row0, vtok, mm_idx, pl.max_eot + n_ctx, f_img, train_labels, scale, loss)
         dvtok = dvtok + self._prompt_set(pl.visual_prompt_temp, None, vtok, v_idx, 1 + n_ctx, f_img, train_labels, scale, loss)
         # ---- aggregator backward
         dagg = torch.zeros(num_cls, T, e, dtype=F32, device=dev)

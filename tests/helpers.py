@@ -84,3 +84,32 @@ def run_generation_and_queries(pair, n_queries: int, structured: bool, exemplar_
     ex, labels, qs, _ = synth_inputs(pair, n_queries, structured)
     return {"gpu": run_product(pair, ex, labels, qs, exemplar_batch_classes),
             "oracle": run_oracle(pair, ex, labels, qs, exemplar_batch_classes)}
+
+
+def check_fusion_outputs(g, o, n_cls: int, shots: int, tau: float, logit_scale, max_flips: int):
+    """Everything downstream of the exemplars' HARD predictions (F1 per class -> softmax(tau F1) fusion weights -> fused
+    probabilities) is a discontinuous function of them, so it is checked in two parts that never skip:
+      * the number of exemplar predictions that differ from the oracle's is bounded (`max_flips`; 0 for class-structured
+        inputs, a handful for plain-noise inputs whose predictions are near-ties);
+      * the integer histograms, the fp32 F1 arithmetic and the fusion softmax are checked EXACTLY by applying the oracle
+        to the product's own predictions, and the fused probabilities against the oracle's classifiers / features
+        combined with those fusion weights.
+    When no prediction flipped the product is also compared with the oracle's own F1 / fusion weights.  Returns flips."""
+    gp, op = g["exemplar_preds"].cpu().long(), o["exemplar_preds"].long()
+    flips = int((gp != op).sum())
+    assert flips <= max_flips, f"{flips} of {gp.numel()} exemplar predictions differ from the oracle's (bound {max_flips})"
+    labels = torch.arange(n_cls).repeat_interleave(shots)
+    f1_own = torch.stack([O.multiclass_f1(gp[:, k], labels, n_cls) for k in range(gp.shape[1])], dim=-1)
+    assert torch.equal(g["f1"].cpu(), f1_own), "F1 from the integer histograms differs from the oracle's F1 of the same predictions"
+    fw_own = (tau * f1_own).softmax(dim=-1)
+    assert (g["fusion_weight"].cpu() - fw_own).abs().max() < 1e-6
+    ref = O.classify(logit_scale, o["query_features"], {"mm_classifier": o["mm_classifier"],
+                                                         "vision_classifier": o["vision_classifier"],
+                                                         "text_classifier": o["text_classifier"], "fusion_weight": fw_own},
+                     "fusion")
+    assert (g["probs"].cpu() - ref).abs().max() < 2e-2
+    if flips == 0:
+        assert torch.equal(g["f1"].cpu(), o["f1"])
+        assert (g["fusion_weight"].cpu() - o["fusion_weight"]).abs().max() < 1e-6
+        assert (g["probs"].cpu() - o["probs"]).abs().max() < 2e-2
+    return flips

@@ -137,16 +137,22 @@ def test_plan_batches_partitions_exactly_and_respects_cap():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """bench.py --impl reference (CPU port of the reference on the host cores): one JSON line with the contract keys."""
+    """bench.py --impl reference (the reference's own CPU implementation on the host cores — its unmodified code when
+    /root/reference or oracle/_ref is present, else the oracle port): one JSON line with the contract keys, labelled
+    with the shape that was actually run."""
     import json
     import subprocess
     import sys
+    from oracle import ref_loader as R
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                          "--cpu-sample-classes", "1", "--shots", "2"], capture_output=True, text=True, timeout=600)
+                          "--cpu-sample-images", "4", "--shots", "2"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "img/s" and line["value"] > 0 and line["higher_is_better"] is True
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] == ("reference" if R.reference_available() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1
+    # --shots 2 is not a BASELINE shape: metric and workload strings must say so instead of claiming config 2
+    assert "x 2 shot" in line["metric"] and line["config"]["workload"].startswith("CUSTOM shape")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0

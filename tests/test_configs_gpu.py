@@ -87,11 +87,8 @@ def test_cfg5_shape_ten_shots_ragged_batches():
     for name in ("text_classifier", "mm_classifier", "vision_classifier"):
         assert _mincos(g[name], o[name]) > 0.999, name
     assert _mincos(g["visual_tokens"].flatten(0, 1), o["visual_tokens"].flatten(0, 1)) > 0.999
-    flips = int((g["exemplar_preds"].cpu().long() != o["exemplar_preds"]).sum())
-    if flips == 0:
-        assert torch.equal(g["f1"].cpu(), o["f1"])
-        assert (g["fusion_weight"].cpu() - o["fusion_weight"]).abs().max() < 1e-6
-        assert (g["probs"].cpu() - o["probs"]).abs().max() < 2e-2
+    from tests.helpers import check_fusion_outputs
+    check_fusion_outputs(g, o, pair.n_cls, pair.shots, pair.tau, pair.sd["logit_scale"].exp(), max_flips=0)
 
 
 # ------------------------------------------------------------------ cfg3: 21,841 classes x 4 shots through the head
@@ -123,6 +120,33 @@ def test_cfg3_many_class_f1_and_fusion_weights():
     ref_f1 = torch.stack([O.multiclass_f1(preds.cpu().long()[:, k], labels, Cn) for k in range(3)], dim=1)
     assert torch.equal(f1.cpu(), ref_f1)
     assert (fw.cpu() - torch.softmax(10.0 * ref_f1, dim=1)).abs().max() < 1e-6
+
+
+# ------------------------------------------------------------------ cfg2 / cfg5 shapes end to end against the fp32 oracle ON THE GPU
+@pytest.mark.parametrize("config,classes,queries", [(2, 64, 4096), (5, 48, 2048)])
+def test_benchmarked_configuration_end_to_end_vs_gpu_fp32_oracle(config, classes, queries):
+    """ViT-B/16 at the benchmarked settings (encoder batch 512, grouped generation, 16 / 10 shots) on a subsample that the
+    fp32 oracle can follow on the GPU (TF32 off): the parity block bench.py prints for every configuration.  Tolerances
+    are BASELINE.json's: cosine >= 0.999, logits within 1e-2, margin-aware top-1 agreement >= 99.5 %, integer outputs
+    exact."""
+    import argparse
+    import bench
+    args = argparse.Namespace(**{k: bench.CONFIGS[config][k] for k in ("backbone", "classes", "shots", "queries", "batch")},
+                              config=config, custom=[], parity_classes=classes, parity_queries=queries)
+    dev = torch.device(DEV)
+    clip_model = bench.build_clip(args, dev)
+    full = bench.build_model(args, clip_model, classes)
+    with torch.no_grad():
+        p = bench.parity_block(args, clip_model, full, dev)
+    assert min(p["min_cos"].values()) >= 0.999, p["min_cos"]
+    assert p["max_abs_dlogit"] <= 1e-2, p["max_abs_dlogit"]
+    assert p["exemplar_prediction_flips"] <= max(2, p["exemplar_predictions"] // 200), p
+    assert p["max_abs_dfusion_weight_given_own_predictions"] < 1e-6
+    assert p["top1_decided_queries"] >= queries // 4 and p["top1_agreement_decided"] >= 0.995, p
+    assert p["topk_bit_exact_on_identical_probs"] and p["topk_mode_equals_api_mode"]
+    assert p["pass"]
+    del full, clip_model
+    torch.cuda.empty_cache()
 
 
 # ------------------------------------------------------------------ cfg2 sizes: properties that need no oracle

@@ -309,6 +309,47 @@ def test_topk_ties_lowest_index():
     assert idx.cpu().tolist() == [[0, 1], [3, 5], [0, 1], [0, 1]]
 
 
+def test_head_survives_nan_rows_and_out_of_range_labels():
+    """A NaN feature row (zero norm / fp16 overflow upstream) must give NaN probabilities like the reference, never an
+    out-of-range index or an out-of-bounds write: top-k indices, argmax predictions and the F1 histograms stay inside
+    [0, C); labels outside [0, C) are skipped by the histogram kernel and reported by the evaluator."""
+    L, lib = _lib()
+    Cn, Cpad, k = 20, 24, 3
+    logits = torch.randn(6, 3 * Cpad)
+    logits[2] = float("nan")
+    logits[4, :Cpad] = float("nan")
+    fw = torch.softmax(torch.randn(Cn, 3), -1)
+    idx = torch.full((6, k), -7, dtype=torch.int32, device=DEV)
+    val = torch.empty(6, k, device=DEV)
+    probs = torch.empty(6, Cn, device=DEV)
+    guard = torch.zeros(4096, dtype=torch.int32, device=DEV)       # lives right behind the histograms below
+    LG, FW = logits.to(DEV), fw.to(DEV)
+    L.check(lib.ovmr_fusion_softmax_topk(LG.data_ptr(), 6, 3 * Cpad, Cpad, 3, Cn, FW.data_ptr(), probs.data_ptr(), Cn, k,
+                                         idx.data_ptr(), val.data_ptr(), L.stream()))
+    preds = torch.full((6, 3), -7, dtype=torch.int32, device=DEV)
+    L.check(lib.ovmr_argmax_segments(LG.data_ptr(), 6, 3 * Cpad, Cpad, 3, Cn, preds.data_ptr(), L.stream()))
+    torch.cuda.synchronize()
+    assert bool(((idx >= 0) & (idx < Cn)).all()) and bool(((preds >= 0) & (preds < Cn)).all())
+    assert bool(torch.isnan(probs[2]).all()) and bool(torch.isfinite(probs[[0, 1, 3, 5]]).all())
+    for r in (0, 1, 3, 5):       # healthy rows are untouched: distinct indices, descending values
+        assert len(set(idx[r].tolist())) == k and bool((val[r, :-1] >= val[r, 1:]).all())
+    # histograms: corrupt predictions / labels are not counted and nothing is written outside the buffer
+    buf = torch.zeros(2 * Cn * 3 + Cn + 64, dtype=torch.int32, device=DEV)
+    bad_pred = preds.clone()
+    bad_pred[0, 0], bad_pred[1, 1] = 0x7fffffff, -5
+    labels = torch.tensor([0, 1, 2, Cn, -1, 3], dtype=torch.int32, device=DEV)
+    L.check(lib.ovmr_f1_counts(bad_pred.data_ptr(), labels.data_ptr(), 6, 3, Cn, buf.data_ptr(), L.stream()))
+    torch.cuda.synchronize()
+    assert int(buf[2 * Cn * 3 + Cn:].abs().sum()) == 0 and int(guard.abs().sum()) == 0
+    assert int(buf[2 * Cn * 3:2 * Cn * 3 + Cn].sum()) == 4            # labels Cn and -1 skipped
+    assert int(buf[Cn * 3:2 * Cn * 3].sum()) == 6 * 3 - 2             # the two corrupt predictions skipped
+    from ovmr_b200.evaluation import Classification
+    ev = Classification(num_classes=Cn, device=DEV)
+    ev.process(preds[:, :1].contiguous(), labels)
+    with pytest.raises(ValueError):
+        ev.evaluate()
+
+
 def test_f1_fusion_weights_match_oracle():
     L, lib = _lib()
     g = torch.Generator().manual_seed(11)

@@ -12,7 +12,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from tests.helpers import GOLDEN, O, build_pair, run_generation_and_queries, run_product, synth_inputs
+from tests.helpers import check_fusion_outputs, GOLDEN, O, build_pair, run_generation_and_queries, run_product, synth_inputs
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -177,12 +177,20 @@ def test_coop_fusion_variant_matches_oracle(tiny, tmp_path):
     feats = O.l2n(O.encode_image(tiny.sd, ex)).reshape(n_cls, shots, -1)
     scale = tiny.sd["logit_scale"].exp()
     fw, f1, preds = O.fusion_weights(scale, feats, ref_cls[0], ref_cls[1], ref_cls[2], 10.0)
-    if bool((model.exemplar_preds.cpu().long() == preds).all()):
+    # hard exemplar predictions: bounded flips, and the derived quantities checked through the oracle applied to the
+    # product's OWN predictions (never skipped)
+    gp = model.exemplar_preds.cpu().long()
+    flips = int((gp != preds).sum())
+    assert flips <= 1, f"{flips} of {gp.numel()} exemplar predictions differ from the oracle's"
+    f1_own = torch.stack([O.multiclass_f1(gp[:, k], labels, n_cls) for k in range(3)], dim=-1)
+    fw_own = (10.0 * f1_own).softmax(dim=-1)
+    assert (model.fusion_weight.cpu() - fw_own).abs().max() < 1e-6
+    ref_probs = O.classify(scale, O.l2n(O.encode_image(tiny.sd, qs)),
+                           {"mm_classifier": ref_cls[0], "vision_classifier": ref_cls[1],
+                            "text_classifier": ref_cls[2], "fusion_weight": fw_own}, "fusion")
+    assert (probs.cpu() - ref_probs).abs().max() < 2e-2
+    if flips == 0:
         assert (model.fusion_weight.cpu() - fw).abs().max() < 1e-6
-        ref_probs = O.classify(scale, O.l2n(O.encode_image(tiny.sd, qs)),
-                               {"mm_classifier": ref_cls[0], "vision_classifier": ref_cls[1],
-                                "text_classifier": ref_cls[2], "fusion_weight": fw}, "fusion")
-        assert (probs.cpu() - ref_probs).abs().max() < 2e-2
         assert (model.fusion_weight.cpu() - torch.from_numpy(gold["fusion_weight"])).abs().max() < 1e-6
         assert (probs.cpu() - torch.from_numpy(gold["probs"])).abs().max() < 2e-2
 
@@ -211,31 +219,29 @@ def test_text_encoder_and_prompt_learner_api(tiny):
     assert _mincos(mm, r_mm) > 0.999 and _mincos(v, r_v) > 0.999
 
 
-def _check_end_to_end(res, golden=None):
+def _check_end_to_end(res, pair, golden=None, max_flips=0):
     g, o = res["gpu"], res["oracle"]
     for name in ("text_classifier", "mm_classifier", "vision_classifier"):
         assert _mincos(g[name], o[name]) > 0.999, name
     assert _mincos(g["visual_tokens"].flatten(0, 1), o["visual_tokens"].flatten(0, 1)) > 0.999
     assert _mincos(g["query_features"], o["query_features"]) > 0.999
     assert _mincos(g["eval_feats"].flatten(0, 1), o["eval_feats"].flatten(0, 1)) > 0.999
-    # fusion weights are a discontinuous function of exemplar predictions: compare them only when the
-    # hard predictions agree, and report flips otherwise
-    flips = int((g["exemplar_preds"].cpu().long() != o["exemplar_preds"]).sum())
-    if flips == 0:
-        assert torch.equal(g["f1"].cpu(), o["f1"])
-        assert (g["fusion_weight"].cpu() - o["fusion_weight"]).abs().max() < 1e-6
-        assert (g["probs"].cpu() - o["probs"]).abs().max() < 2e-2
-    if golden is not None and flips == 0:
-        assert (g["fusion_weight"].cpu() - torch.from_numpy(golden["fusion_weight"])).abs().max() < 1e-6
+    # fusion weights are a discontinuous function of the exemplars' hard predictions: the flips are bounded
+    # and everything derived from the predictions is checked exactly through the oracle applied to the product's own
+    # predictions (tests/helpers.check_fusion_outputs) — no assertion is skipped when a prediction flips
+    flips = check_fusion_outputs(g, o, pair.n_cls, pair.shots, pair.tau, pair.sd["logit_scale"].exp(), max_flips)
+    if golden is not None:
         for name in ("text_classifier", "mm_classifier", "vision_classifier"):
             assert _mincos(g[name], torch.from_numpy(golden[name])) > 0.999, name
+        if flips == 0:
+            assert (g["fusion_weight"].cpu() - torch.from_numpy(golden["fusion_weight"])).abs().max() < 1e-6
     return flips
 
 
 def test_end_to_end_tiny_structured(tiny):
     res = run_generation_and_queries(tiny, n_queries=32, structured=True)
     gold = np.load(os.path.join(GOLDEN, "tiny_c6s3_structured.npz"))
-    flips = _check_end_to_end(res, gold)
+    flips = _check_end_to_end(res, tiny, gold, max_flips=0)
     g, o = res["gpu"], res["oracle"]
     agree = (g["probs"].argmax(1).cpu() == o["probs"].argmax(1))
     top2 = o["probs"].topk(2, dim=1).values
@@ -246,7 +252,7 @@ def test_end_to_end_tiny_structured(tiny):
 def test_end_to_end_tiny_two_exemplar_batches(tiny):
     """Loop B with several class-contiguous batches (RandomClassSampler contract) gives the same classifiers."""
     res = run_generation_and_queries(tiny, n_queries=16, structured=True, exemplar_batch_classes=2)
-    _check_end_to_end(res)
+    _check_end_to_end(res, tiny, max_flips=0)
 
 
 def test_artifacts_layout(tiny, tmp_path):
@@ -272,10 +278,11 @@ def test_artifacts_layout(tiny, tmp_path):
 def test_end_to_end_vitb16_cfg1(structured):
     """BASELINE config 1 (ViT-B/16, 10 classes x 4 shots) against the oracle and the reference goldens."""
     pair = build_pair("ViT-B/16", n_cls=10, shots=4, device=DEV)
-    nq = 64
-    res = run_generation_and_queries(pair, n_queries=nq, structured=structured)
     gold = np.load(os.path.join(GOLDEN, "vitb16_cfg1_structured.npz" if structured else "vitb16_cfg1.npz"))
-    flips = _check_end_to_end(res, gold)
+    nq = int(gold["Q"])          # every golden query: 256 (plain noise) / 64 (class-structured)
+    res = run_generation_and_queries(pair, n_queries=nq, structured=structured)
+    # plain-noise exemplars are near-ties for every classifier: allow 2 of the 120 hard predictions to differ (measured: 0)
+    flips = _check_end_to_end(res, pair, gold, max_flips=0 if structured else 2)
     g, o = res["gpu"], res["oracle"]
     assert _mincos(g["query_features"][:32], torch.from_numpy(gold["query_features"])[:32]) > 0.999
     # logits within 1e-2 (bf16 tolerance of BASELINE.json): recompute the three cosine logits from features
@@ -284,11 +291,16 @@ def test_end_to_end_vitb16_cfg1(structured):
         lg = s * g["query_features"].cpu() @ g[name].cpu().t()
         lo = s * o["query_features"] @ o[name].t()
         assert (lg - lo).abs().max() < 1e-2, name
-    if structured:
-        assert flips == 0
-        top2 = o["probs"].topk(2, dim=1).values
-        decided = (top2[:, 0] - top2[:, 1]) > 2e-2
-        agree = g["probs"].argmax(1).cpu() == o["probs"].argmax(1)
+    # the reference's own fused probabilities / argmax on all golden queries
+    gp = torch.from_numpy(gold["fused_probs"])
+    if flips == 0:
+        assert (g["probs"].cpu() - gp).abs().max() < 2e-2
+    top2 = gp.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 2e-2
+    agree = g["probs"].argmax(1).cpu() == torch.from_numpy(gold["argmax"]).long()
+    if bool(decided.any()):
         assert agree[decided].float().mean() >= 0.995
+    if structured:
+        assert flips == 0 and int(decided.sum()) >= nq // 2      # the structured set is the well-conditioned one
     del pair
     torch.cuda.empty_cache()
