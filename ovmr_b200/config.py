@@ -16,13 +16,24 @@ class CN(dict):
 
 
 def make_cfg(n_ctx=2, shots=16, image_size=224, eval_mode="fusion", eval_tau=10, output_dir=None,
-             backbone="ViT-B/16", batch_size=256, n_ins=16, prec="fp16"):
+             backbone="ViT-B/16", batch_size=256, n_ins=16, prec="fp16", test_batch_size=256, dataset=None,
+             trainer="MM_CLS_OP", optim=None, init_weights=""):
     """Defaults follow configs/trainers/MM_CLS_OP/vit_b16_c4_ep50_imagenet21k_pretrain.yaml and
-    scripts/mm_cls/generate_classifier.sh of the reference."""
-    return CN(TRAINER=CN(COCOOP=CN(N_CTX=n_ctx, PREC=prec)), INPUT=CN(SIZE=(image_size, image_size)),
-              DATALOADER=CN(TRAIN_X=CN(BATCH_SIZE=batch_size, N_INS=n_ins), K_TRANSFORMS=1),
-              DATASET=CN(NUM_SHOTS=shots), EVAL_MODE=eval_mode, EVAL_TAU=eval_tau, OUTPUT_DIR=output_dir,
-              MODEL=CN(BACKBONE=CN(NAME=backbone)))
+    scripts/mm_cls/generate_classifier.sh of the reference; keys the yaml does not set carry Dassl's defaults
+    (dassl/config/defaults.py).  `dataset`: dict of cfg.DATASET entries (NAME, NUM_CLASSES, ... for ovmr_b200.runner);
+    `optim`: dict overriding the yaml's OPTIM block."""
+    optim_cfg = CN(NAME="adam", LR=0.0002, MAX_EPOCH=30, LR_SCHEDULER="cosine", WARMUP_EPOCH=1, WARMUP_TYPE="constant",
+                   WARMUP_CONS_LR=1e-5)
+    optim_cfg.update(optim or {})
+    ds = CN(NUM_SHOTS=shots, REGION_AUG=False)
+    ds.update(dataset or {})
+    return CN(TRAINER=CN(NAME=trainer, COCOOP=CN(N_CTX=n_ctx, PREC=prec)), INPUT=CN(SIZE=(image_size, image_size)),
+              DATALOADER=CN(TRAIN_X=CN(BATCH_SIZE=batch_size, N_INS=n_ins, SAMPLER="RandomClassSampler"),
+                            TEST=CN(BATCH_SIZE=test_batch_size, SAMPLER="SequentialSampler", N_INS=shots),
+                            K_TRANSFORMS=1, NUM_WORKERS=0),
+              DATASET=ds, EVAL_MODE=eval_mode, EVAL_TAU=eval_tau, OUTPUT_DIR=output_dir,
+              MODEL=CN(BACKBONE=CN(NAME=backbone), INIT_WEIGHTS=init_weights), OPTIM=optim_cfg,
+              TRAIN=CN(PRINT_FREQ=10, CHECKPOINT_FREQ=10), TEST=CN(NO_TEST=True, SPLIT="test"), USE_CUDA=True, SEED=1)
 
 
 class Precision:

@@ -92,3 +92,23 @@ class GpuTransform:
                                         self._tmp.data_ptr(), self._tmp.numel(), dst.data_ptr(), L.stream()),
                 "ovmr_resize_crop_u8")
         return dst
+
+
+def clip_transform_or_identity(n_px: int):
+    """Per-item transform of the Dassl-shaped loaders (ovmr_b200.runner): tensors pass through (in-memory datasets
+    already hold model inputs); a file path is decoded with Pillow, resized (smaller edge -> n_px, BICUBIC) and
+    centre-cropped exactly as the reference's `_transform` does on the host (clip/clip.py:73-78), and returned as the
+    uint8 [3, n_px, n_px] crop — ToTensor + Normalize are fused into the image tower's patch load on the device."""
+    def tf(src):
+        if isinstance(src, torch.Tensor):
+            return src
+        from PIL import Image
+        img = Image.open(src).convert("RGB")
+        w, h = img.size
+        oh, ow = resized_size(h, w, n_px)
+        if (oh, ow) != (h, w):
+            img = img.resize((ow, oh), Image.BICUBIC)
+        top, left = center_crop_origin(oh, ow, n_px)
+        img = img.crop((left, top, left + n_px, top + n_px))
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(img, dtype=np.uint8).transpose(2, 0, 1)))
+    return tf

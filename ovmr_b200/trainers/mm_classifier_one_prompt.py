@@ -363,56 +363,95 @@ class CustomCLIP(nn.Module):
         return probs
 
 
-class _Registry(dict):
-    def register(self, cls=None):
-        def deco(c):
-            self[c.__name__] = c
-            return c
-        return deco(cls) if cls is not None else deco
-
-
-try:  # use Dassl's registry when the caller has Dassl installed (it is not part of this build)
-    from dassl.engine import TRAINER_REGISTRY  # type: ignore
-except Exception:  # pragma: no cover
-    TRAINER_REGISTRY = _Registry()
+from ..runner import TRAINER_REGISTRY, TrainerX, lr_schedule, optim_settings  # noqa: E402
 
 
 @TRAINER_REGISTRY.register()
-class MM_CLS_OP:
-    """Eval-side shell of the reference trainer (trainers/...:367-493): build_model / load_model /
-    model_inference with the same names.  The optimisation loop (forward_backward) is out of scope."""
+class MM_CLS_OP(TrainerX):
+    """The reference trainer (trainers/...:366-493) on the Dassl-shaped life cycle of ovmr_b200.runner:
 
-    def __init__(self, cfg, classnames: List[str], device="cuda"):
-        self.cfg = cfg
-        self.classnames = classnames
-        self.device = torch.device(device)
-        self.check_cfg(cfg)
-        self.build_model()
+        trainer = MM_CLS_OP(cfg)                       # loaders from cfg.DATASET, classnames from self.dm.dataset
+        trainer.load_model(model_dir, epoch=30); trainer.test()          # train.py --eval-only
+        trainer.train()                                                  # token-generator training
+
+    `MM_CLS_OP(cfg, classnames, device)` (no dataset: an eval-side shell whose caller supplies the loaders) is kept for
+    code that drives `model_inference` / `forward_backward` directly."""
+
+    def __init__(self, cfg, classnames: Optional[List[str]] = None, device=None, dataset=None):
+        self._classnames_arg = classnames
+        self._device_arg = device
+        if classnames is None:
+            super().__init__(cfg, dataset=dataset)
+        else:   # shell without a data manager
+            from collections import OrderedDict
+            self._models, self._optims, self._scheds = OrderedDict(), OrderedDict(), OrderedDict()
+            self.check_cfg(cfg)
+            self.cfg = cfg
+            self.device = torch.device(device or "cuda")
+            self.start_epoch = self.epoch = 0
+            self.batch_idx, self.num_batches = 0, 1
+            self.max_epoch = int(optim_settings(getattr(cfg, "OPTIM", None)).MAX_EPOCH)
+            self.output_dir = getattr(cfg, "OUTPUT_DIR", None)
+            self.dm = None
+            self.eval_set_loader = None
+            self.build_model()
+
+    @property
+    def classnames(self):
+        return self._classnames_arg if self._classnames_arg is not None else self.dm.dataset.classnames
 
     def check_cfg(self, cfg):
         assert cfg.TRAINER.COCOOP.PREC in ["fp16", "fp32", "amp"]
 
     def build_model(self):
+        """trainers/...:372-419.  The optimiser is the native Adam of ovmr_b200.training driven by cfg.OPTIM (name, LR,
+        weight decay, betas) and Dassl's per-epoch LR schedule; only prompt_learner parameters are trainable."""
         cfg = self.cfg
         clip_model = load_clip_to_cpu(cfg).to(self.device)
         self.model = CustomCLIP(cfg, self.classnames, clip_model).eval()
         for name, param in self.model.named_parameters():
             if "prompt_learner" not in name:
                 param.requires_grad_(False)
+        init = getattr(getattr(cfg, "MODEL", None), "INIT_WEIGHTS", "")
+        if init:
+            sd = torch.load(init, map_location="cpu")
+            self.model.prompt_learner.load_state_dict(sd.get("state_dict", sd), strict=False)
+        self._optim()
+        self.register_model("prompt_learner", self.model.prompt_learner, None, None)
+
+    def _optim(self):
+        """cfg.OPTIM completed with Dassl's defaults + the per-epoch LR list (built on first use)."""
+        o = self.__dict__.get("optim_cfg")
+        if o is None:
+            o = optim_settings(getattr(self.cfg, "OPTIM", None))
+            if o.NAME != "adam":
+                raise ValueError(f"MM_CLS_OP: OPTIM.NAME={o.NAME!r} is not supported by the native training step "
+                                 "(the reference's configs use 'adam')")
+            self.optim_cfg, self._lrs, self._sched_epoch = o, lr_schedule(o), 0
+        return o
+
+    # ---- LR schedule (stepped once per epoch, after its last batch: trainers/...:449-450)
+    def get_current_lr(self, names=None):
+        o = self._optim()
+        return self._lrs[min(self._sched_epoch, len(self._lrs) - 1)] if self._lrs else float(o.LR)
+
+    def update_lr(self, names=None):
+        self._optim()
+        self._sched_epoch += 1
+
+    def _native_trainer(self):
+        o = self._optim()
+        return self.model.trainer(lr=float(o.LR), betas=(float(o.ADAM_BETA1), float(o.ADAM_BETA2)),
+                                  weight_decay=float(o.WEIGHT_DECAY))
 
     def forward_backward(self, batch):
-        """trainers/...:421-452: one optimisation step of the visual token generator (native loss, gradients and
-        Adam; cfg.OPTIM.LR / MAX_EPOCH drive the cosine schedule when present)."""
+        """trainers/...:421-452: one optimisation step of the visual token generator (native loss, gradients, Adam with
+        cfg.OPTIM's weight decay / betas) at the current epoch's LR; the schedule advances after the epoch's last batch."""
         image, label = self.parse_batch_train(batch)
         self.model.prompt_learner.train()
-        optim = getattr(self.cfg, "OPTIM", None)
-        base_lr = float(getattr(optim, "LR", 2e-4)) if optim is not None else 2e-4
-        tr = self.model.trainer(lr=base_lr)
-        lr = base_lr
-        if optim is not None and getattr(optim, "MAX_EPOCH", 0):
-            from ..training import cosine_lr
-            lr = cosine_lr(base_lr, int(getattr(self, "epoch", 0)), int(optim.MAX_EPOCH))
-        loss = tr.step(image, label, lr=lr)
+        loss = self._native_trainer().step(image, label, lr=self.get_current_lr())
+        if (getattr(self, "batch_idx", 0) + 1) == getattr(self, "num_batches", 1):
+            self.update_lr()
         return {"loss": loss}
 
     def parse_batch_train(self, batch):
@@ -444,7 +483,12 @@ class MM_CLS_OP:
         return fpath
 
     def model_inference(self, input, scale_no=None, label=None, eval_set_loader=None):
-        return self.model(input, eval_set_loader=eval_set_loader, scale_no=scale_no, label=label)
+        """dassl/engine/trainer.py:509-513.  Inference always runs the eval branch: Dassl's test() calls
+        set_model_mode("eval") first, and a caller that goes straight from forward_backward to model_inference must not
+        fall into the training branch of CustomCLIP.forward."""
+        self.model.prompt_learner.eval()
+        loader = eval_set_loader if eval_set_loader is not None else getattr(self, "eval_set_loader", None)
+        return self.model(input, eval_set_loader=loader, scale_no=scale_no, label=label)
 
     def load_model(self, directory, epoch=None):
         """trainers/...:461-493 — prompt_learner/model.pth.tar-<epoch> ({state_dict, epoch, ...}), strict=False,
