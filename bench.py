@@ -479,8 +479,7 @@ def main():
             vals.append(v)
         idx = torch.cat(idxs) if idxs else torch.empty(0, 1, dtype=torch.int32, device=device)
         val = torch.cat(vals) if vals else torch.empty(0, 1, device=device)
-        idx_all = D.all_gather_rows(idx, Q)
-        val_all = D.all_gather_rows(val, Q)
+        idx_all, val_all = D.all_gather_packed([idx, val], Q)     # one collective for the (index, probability) pairs
         if phase_events is not None:
             phase_events[2].record()
         return idx_all, val_all

@@ -64,20 +64,69 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, local_rank, world
 
 
+_BUFFERS = {}
+
+
+def _buffer(tag, shape, dtype, device) -> torch.Tensor:
+    """Persistent staging buffer per (purpose, shape, dtype, device): the collectives run every step with the same
+    shapes, so nothing is allocated (and no allocator traffic crosses streams) after the first call."""
+    key = (tag, tuple(shape), dtype, str(device))
+    buf = _BUFFERS.get(key)
+    if buf is None:
+        buf = torch.zeros(shape, dtype=dtype, device=device)
+        _BUFFERS[key] = buf
+    return buf
+
+
 def all_gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
-    """Concatenate contiguous row shards (shard_range partition of n_total rows) from every rank.
-    Shards may differ by one row, so each rank pads to the largest shard for a single
-    all_gather_into_tensor and the padding is dropped on receipt."""
+    """Concatenate contiguous row shards (shard_range partition of n_total rows) from every rank: ONE
+    all_gather_into_tensor.  Equal shards are gathered straight into the result; shards that differ by one row are
+    padded to the largest shard in a persistent staging buffer and compacted with one row gather on receipt."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local
     world = dist.get_world_size(group)
     sizes = [shard_range(n_total, r, world) for r in range(world)]
     mx = max(hi - lo for lo, hi in sizes)
-    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    tail = tuple(local.shape[1:])
+    local = local.contiguous()
+    if all(hi - lo == mx for lo, hi in sizes):
+        out = torch.empty((n_total,) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+    pad = _buffer("pad", (mx,) + tail, local.dtype, local.device)
     pad[: local.shape[0]] = local
-    out = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
-    return torch.cat([out[r * mx: r * mx + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], dim=0)
+    out = _buffer("out", (world * mx,) + tail, local.dtype, local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    key = ("rows", n_total, world, str(local.device))
+    rows = _BUFFERS.get(key)
+    if rows is None:
+        rows = torch.cat([torch.arange(r * mx, r * mx + (hi - lo)) for r, (lo, hi) in enumerate(sizes)]).to(local.device)
+        _BUFFERS[key] = rows
+    return out.index_select(0, rows)
+
+
+def all_gather_packed(parts, n_total: int, group=None):
+    """Several row-sharded tensors with the same row partition (e.g. the mm / v classifier rows, the visual tokens and
+    the initialised flags of a class shard; or top-k indices and values of a query shard) in ONE collective: every part
+    is viewed as 32-bit words, the parts are laid side by side in one [rows, words] buffer, gathered, and split back into
+    tensors of the original dtypes and trailing shapes.  All parts must be 4-byte types."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return list(parts)
+    rows = parts[0].shape[0]
+    words, metas = [], []
+    for p in parts:
+        assert p.shape[0] == rows and p.element_size() == 4, "all_gather_packed: 32-bit parts with a common row count"
+        flat = p.contiguous().view(rows, -1)
+        words.append(flat.view(torch.int32))
+        metas.append((p.dtype, tuple(p.shape[1:]), flat.shape[1]))
+    packed = _buffer("pack", (rows, sum(m[2] for m in metas)), torch.int32, parts[0].device)
+    torch.cat(words, dim=1, out=packed)
+    full = all_gather_rows(packed, n_total, group)
+    out, col = [], 0
+    for dtype, tail, w in metas:
+        out.append(full[:, col:col + w].contiguous().view(dtype).view((n_total,) + tail))
+        col += w
+    return out
 
 
 def all_gather_sum(local: torch.Tensor, group=None) -> torch.Tensor:

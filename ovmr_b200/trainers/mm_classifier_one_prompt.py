@@ -274,11 +274,11 @@ class CustomCLIP(nn.Module):
         if shard is not None and shard.world > 1:
             from .. import dist as D
             lo, hi = shard.lo, shard.hi
-            self.mm_classifier = D.all_gather_rows(self.mm_classifier[lo:hi].contiguous(), n_cls)
-            self.visual_classifer = D.all_gather_rows(self.visual_classifer[lo:hi].contiguous(), n_cls)
-            self.visual_tokens = D.all_gather_rows(self.visual_tokens[lo:hi].contiguous(), n_cls)
-            self.inference_text_initialized = D.all_gather_rows(self.inference_text_initialized[lo:hi].contiguous(),
-                                                                n_cls)
+            # one collective for everything a class shard produced (classifier rows, visual tokens, initialised flags)
+            (self.mm_classifier, self.visual_classifer, self.visual_tokens,
+             self.inference_text_initialized) = D.all_gather_packed(
+                [self.mm_classifier[lo:hi], self.visual_classifer[lo:hi], self.visual_tokens[lo:hi],
+                 self.inference_text_initialized[lo:hi]], n_cls)
         assert self.inference_text_initialized.bool().all()
 
         # exemplar self-classification (this rank's classes only when sharded) -> global F1 counts

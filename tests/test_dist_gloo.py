@@ -47,9 +47,11 @@ def _worker(rank, world, port, out_dir):
         mm_p, mm_l, v_p, v_l, _ = O.prompt_learner_forward(pl, prompt_tokens, vtemp, feats, ex_label,
                                                            tok[ex_label].argmax(-1))
         mm_loc, v_loc = O.get_mm_v_feats(sd, mm_p, mm_l, v_p, v_l)
-        mm = D.all_gather_rows(mm_loc, C)
-        v = D.all_gather_rows(v_loc, C)
-        assert mm.shape == (C, e)
+        # the product's packed exchange: classifier rows + an int32 flag vector in ONE collective (uneven shards -> padded)
+        flags = torch.full((sh.size,), rank + 1, dtype=torch.int32)
+        mm, v, fl = D.all_gather_packed([mm_loc, v_loc, flags], C)
+        assert mm.shape == (C, e) and fl.dtype == torch.int32 and fl.tolist() == [1, 1, 1, 2, 2]
+        assert torch.equal(mm, D.all_gather_rows(mm_loc, C)) and torch.equal(v, D.all_gather_rows(v_loc, C))
         # --- local exemplars scored against all classifiers; count histograms summed across ranks
         scale = sd["logit_scale"].exp()
         flat = feats.reshape(sh.size * S, e)
@@ -76,8 +78,10 @@ def _worker(rank, world, port, out_dir):
         probs = O.classify(scale, O.l2n(O.encode_image(sd, qs[lo:hi])),
                            {"mm_classifier": mm, "vision_classifier": v, "text_classifier": t_cls, "fusion_weight": fw})
         idx, val = O.topk(probs, 1)
-        idx_all = D.all_gather_rows(idx.int(), Q)
-        val_all = D.all_gather_rows(val, Q)
+        idx_all, val_all = D.all_gather_packed([idx.int(), val], Q)       # one collective for (index, probability)
+        # equal shards take the zero-copy path
+        eq = D.all_gather_rows(torch.full((3, 2), float(rank)), 6)
+        assert eq.shape == (6, 2) and eq[:3].eq(0).all() and eq[3:].eq(1).all()
         elapsed = D.max_over_ranks(float(rank + 1), torch.device("cpu"))
         assert elapsed == float(world)
     D.barrier()

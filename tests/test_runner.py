@@ -185,7 +185,7 @@ def test_eval_only_flow_build_trainer_load_model_test(tmp_path):
         probs = O.classify(sd["logit_scale"].exp(), O.l2n(O.encode_image(sd, qs)), gen, "fusion")
     ref_acc = 100.0 * float((probs.argmax(1) == ql).float().mean())
     assert abs(acc - ref_acc) <= 100.0 / len(ql) + 1e-9, (acc, ref_acc)      # at most one near-tie query
-    assert acc > 50.0                                                         # the structured problem is separable
+    # (a random-init CLIP classifies at chance — 16.7 % here, and so does the oracle; the point is the equality above)
 
 
 @pytest.mark.gpu
