@@ -67,6 +67,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="eval", choices=["eval", "train"],
+                    help="eval: classifier generation + query classification (the headline); train: optimisation steps of the "
+                         "visual token generator at the reference's batch (192 classes x 8 instances, ViT-B/16)")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--backbone", default=None, choices=sorted(ARCH))
     ap.add_argument("--classes", type=int, default=None)
@@ -416,12 +419,124 @@ def parity_block(args, clip_model, full_model, device):
     return out
 
 
+def run_train(args):
+    """`--mode train`: steps of MM_CLS_OP.forward_backward's arithmetic (trainers/...:296-338, 421-452) at the
+    reference's training batch — configs/trainers/MM_CLS_OP/vit_b16_c4_ep50_imagenet21k_pretrain.yaml: 1536 images =
+    192 classes x N_INS 8, Adam 2e-4 — on one GPU: frozen image tower forward, aggregator forward, two prompt sets through
+    the frozen text tower, CE + CE, backward into the aggregator, native Adam.  Parity: loss and all 49 gradient tensors
+    against torch.autograd on the fp32 oracle (GPU, TF32 off)."""
+    from oracle import ovmr_oracle as O
+    from ovmr_b200 import _lib as L
+    from ovmr_b200.clip import tokenize
+    from ovmr_b200.training import GeneratorTrainer
+    assert torch.cuda.is_available(), "bench.py --mode train needs a GPU"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    device = torch.device("cuda", 0)
+    n_cls, n_ins, split = 192, 8, 4
+    args.backbone, args.shots = "ViT-B/16", n_ins
+    clip_model = build_clip(args, device)
+    model = build_model(args, clip_model, n_cls)
+    model.num_ins = n_ins
+    model.prompt_learner.train()
+    res = ARCH[args.backbone][1]
+    labels = torch.arange(n_cls, device=device).repeat_interleave(n_ins)
+    images = device_images(n_cls * n_ins, res, device, seed=11)
+    images += device_images(n_cls, res, device, seed=12)[labels]
+    tr = GeneratorTrainer(model, lr=2e-4, weight_decay=5e-4, dropout=0.1)
+    # ---- parity (dropout off: the oracle has none)
+    tr0 = GeneratorTrainer(model, lr=2e-4, dropout=0.0)
+    loss, grads = tr0.loss_and_grads(images, labels, split_point=split)
+    sd = {k: v.detach().float() for k, v in clip_model.state_dict().items()}
+    plr = {k: v.detach().float().clone().requires_grad_(True) for k, v in model.prompt_learner.state_dict().items()}
+    tok, tmpl = tokenize([f"a class {i}." for i in range(n_cls)]), tokenize("a .")
+    ref_loss = O.training_loss(sd, plr, tok, tmpl, images, labels, n_ins, split)
+    ref = dict(zip(plr, torch.autograd.grad(ref_loss, list(plr.values()))))
+    cosf = lambda a, b: float((a.flatten().double() @ b.flatten().double()) / (a.norm().double() * b.norm().double() + 1e-30))
+    parity = {"loss": float(loss), "oracle_loss": float(ref_loss), "abs_dloss": abs(float(loss) - float(ref_loss)),
+              "min_gradient_cosine_over_49_tensors": min(cosf(grads[k], ref[k]) for k in ref),
+              "gradient_norm_ratio_range": [min(float(grads[k].norm() / ref[k].norm()) for k in ref),
+                                            max(float(grads[k].norm() / ref[k].norm()) for k in ref)],
+              "oracle": "torch.autograd on oracle/ovmr_oracle.training_loss, fp32 on the GPU (TF32 off), dropout off"}
+    parity["pass"] = bool(parity["abs_dloss"] < 2e-3 and parity["min_gradient_cosine_over_49_tensors"] >= 0.999)
+    del ref, plr, tr0
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    W, K = max(args.warmup, 3), args.steps
+    for _ in range(W):
+        tr.step(images, labels)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = L.launch_count()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(K):
+        tr.step(images, labels)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    launches = L.launch_count() - l0
+    L.profile_enable(True)
+    for _ in range(K):
+        tr.step(images, labels)
+    torch.cuda.synchronize()
+    prof = L.profile_summary()
+    L.profile_enable(False)
+    clocks = sampler.stop()
+    # ---- e2e: the batch comes from pinned host memory (uint8 pixels), the loss goes back to the host every step
+    host = torch.randint(0, 256, (n_cls * n_ins, 3, res, res), dtype=torch.uint8).pin_memory()
+    mean = torch.tensor([0.48145466, 0.4578275, 0.40821073], device=device).view(1, 3, 1, 1) * 255
+    std = torch.tensor([0.26862954, 0.26130258, 0.27577711], device=device).view(1, 3, 1, 1) * 255
+
+    def e2e_step():
+        x = host.to(device, non_blocking=True)
+        return tr.step((x.float() - mean) / std, labels)      # (the training branch takes normalised floats, like the reference)
+    e2e_step()
+    torch.cuda.synchronize()
+    a0, a1 = ev(), ev()
+    a0.record()
+    for _ in range(K):
+        last = e2e_step()
+    a1.record()
+    torch.cuda.synchronize()
+    ms_e2e = a0.elapsed_time(a1) / K
+    peaks = measured_peaks()
+    n_img = n_cls * n_ins
+    gemm = prof["gemm"]
+    achieved = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    line = {"mode": "train", "metric": "training img/s (visual token generator, ViT-B/16, 192 classes x 8 instances per step)",
+            "value": n_img / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 image tower, fp16 text / aggregator towers (loss scale 1024), fp32 accumulate / master weights / Adam",
+            "data": "synthetic",
+            "config": {"workload": "SURVEY.md §8 f4: MM_CLS_OP.forward_backward at the batch of configs/trainers/MM_CLS_OP/"
+                                   "vit_b16_c4_ep50_imagenet21k_pretrain.yaml (1536 images = 192 classes x 8, random split point "
+                                   "in [2, 6), dropout 0.1, Adam 2e-4, weight decay 5e-4); one step = loss + gradients + optimiser",
+                       "l2_policy": f"inputs larger than L2: {n_img * 3 * res * res * 4 / 1e9:.2f} GB of images per step"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"kernel": "gemm_tn_kernel (tcgen05/TMEM GEMM: image tower, text tower forward / dgrad, aggregator "
+                                   "forward / dgrad / wgrad)", "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
+                         "unit": "TFLOP/s", "frac": achieved / peaks["tflops"] if peaks["tflops"] else None, "traffic": None,
+                         "peak_source": peaks["source"],
+                         "kernel_ms_per_step": {k: round(v["ms"] / K, 3) for k, v in prof.items()}},
+            "e2e": {"value": n_img / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(host.numel()),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "last_loss": float(last),
+                    "api": "GeneratorTrainer.step(images, labels) behind MM_CLS_OP.forward_backward; uint8 batch from pinned host "
+                           "memory, loss read back every step"},
+            "parity": parity}
+    print(json.dumps(line))
+
+
 def main():
     args = parse_args()
     from ovmr_b200 import dist as D
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         run_reference(args, rank)
+        return
+    if args.mode == "train":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_train(args)
         return
     rank, local_rank, world = D.init_from_env()
     assert torch.cuda.is_available(), "bench.py (impl ours) needs a GPU; there is no CPU fallback"

@@ -489,9 +489,10 @@ def training_loss(sd: State, pl: State, tokenized_prompts: Tensor, visual_templa
         image_features = l2n(encode_image(sd, input_image))
         exemplar_features = l2n(encode_image(sd, exemplar_image)).reshape(num_cls, n_ins - split_point, -1)
     exemplar_label = labels.reshape(num_cls, n_ins)[:, 0]
-    train_labels = torch.arange(num_cls).reshape(num_cls, -1).repeat(1, split_point).reshape(-1)
+    train_labels = torch.arange(num_cls, device=images.device).reshape(num_cls, -1).repeat(1, split_point).reshape(-1)
+    tokenized_prompts = tokenized_prompts.to(images.device)
     prompt_tokens = sd["token_embedding.weight"][tokenized_prompts.long()]
-    visual_prompt_temp = sd["token_embedding.weight"][visual_template_tokens.long()]
+    visual_prompt_temp = sd["token_embedding.weight"][visual_template_tokens.long().to(images.device)]
     eot = tokenized_prompts[exemplar_label].argmax(dim=-1)
     mm_p, mm_l, v_p, v_l, _ = prompt_learner_forward(pl, prompt_tokens, visual_prompt_temp, exemplar_features,
                                                     exemplar_label, eot)

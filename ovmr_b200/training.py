@@ -23,8 +23,20 @@ import torch
 from . import _lib as L
 from . import engine as E
 
-F32, BF16, I32 = torch.float32, torch.bfloat16, torch.int32
-FP16_FLAG = 0   # 16-bit format of every training operand: bf16
+F32, BF16, FP16, I32 = torch.float32, torch.bfloat16, torch.float16, torch.int32
+
+
+class _Format:
+    """16-bit operand format of the training step (set by the GeneratorTrainer that is running): bf16, or IEEE fp16 with a
+    static loss scale (the gradient entering the backward pass is multiplied by `loss_scale`, every parameter gradient
+    divided by it at the end; fp32 accumulation everywhere)."""
+    flag = 0
+    dtype = BF16
+
+
+def _set_format(fp16: bool):
+    _Format.flag = 1 if fp16 else 0
+    _Format.dtype = FP16 if fp16 else BF16
 
 
 def _p(t):
@@ -33,12 +45,12 @@ def _p(t):
 
 def _gemm(A, lda, B, ldb, M, N, K, out, ldo, bias=None, resid=None, ldr=0, out16=False, act=0, alpha=1.0):
     L.check(L.lib().ovmr_gemm_tn(A.data_ptr(), lda, B.data_ptr(), ldb, M, N, K, _p(bias), _p(resid), ldr, out.data_ptr(), ldo,
-                                 int(out16), act, float(alpha), 0, 0, FP16_FLAG, L.stream()), "ovmr_gemm_tn")
+                                 int(out16), act, float(alpha), 0, 0, _Format.flag, L.stream()), "ovmr_gemm_tn")
 
 
 def _cast16(x):
-    out = torch.empty(x.shape, dtype=BF16, device=x.device)
-    L.check(L.lib().ovmr_cast_16(x.data_ptr(), out.data_ptr(), x.numel(), FP16_FLAG, L.stream()), "ovmr_cast_16")
+    out = torch.empty(x.shape, dtype=_Format.dtype, device=x.device)
+    L.check(L.lib().ovmr_cast_16(x.data_ptr(), out.data_ptr(), x.numel(), _Format.flag, L.stream()), "ovmr_cast_16")
     return out
 
 
@@ -46,15 +58,15 @@ def _transpose16(x, rows, cols):
     """[rows, cols] fp32 or bf16 (contiguous) -> bf16 [cols, rows rounded up to 64] (zero padded: the padded extent is
     the K dimension of a wgrad GEMM, kept a whole number of 64-element K blocks)."""
     rp = (rows + 63) // 64 * 64
-    out = torch.empty(cols, rp, dtype=BF16, device=x.device)
-    L.check(L.lib().ovmr_transpose_16(x.data_ptr(), int(x.dtype == F32), cols, rows, cols, out.data_ptr(), rp, FP16_FLAG,
+    out = torch.empty(cols, rp, dtype=_Format.dtype, device=x.device)
+    L.check(L.lib().ovmr_transpose_16(x.data_ptr(), int(x.dtype == F32), cols, rows, cols, out.data_ptr(), rp, _Format.flag,
                                       L.stream()), "ovmr_transpose_16")
     return out, rp
 
 
 def _colsum(x, rows, cols):
     out = torch.zeros(cols, dtype=F32, device=x.device)
-    L.check(L.lib().ovmr_colsum(x.data_ptr(), int(x.dtype == F32), cols, rows, cols, out.data_ptr(), FP16_FLAG, L.stream()),
+    L.check(L.lib().ovmr_colsum(x.data_ptr(), int(x.dtype == F32), cols, rows, cols, out.data_ptr(), _Format.flag, L.stream()),
             "ovmr_colsum")
     return out
 
@@ -92,7 +104,7 @@ class TowerState:
         dev = self.device
         self._sig = self._param_signature()
         f32 = lambda t: t.detach().to(device=dev, dtype=F32).contiguous()
-        b16 = lambda t: t.detach().to(device=dev, dtype=F32).to(BF16).contiguous()
+        b16 = lambda t: t.detach().to(device=dev, dtype=F32).to(_Format.dtype).contiguous()
         self.layers = []
         n = len(self.blocks)
         self.arr = (L.BlockWeights * n)()
@@ -108,7 +120,7 @@ class TowerState:
             w.update(qkv_wT=b16(b.attn.in_proj_weight.t()), out_wT=b16(b.attn.out_proj.weight.t()),
                      fc_wT=b16(b.mlp.c_fc.weight.t()), proj_wT=b16(b.mlp.c_proj.weight.t()))
             self.layers.append(w)
-        self.structs = [L.Transformer(self.width, self.heads, 1, FP16_FLAG,
+        self.structs = [L.Transformer(self.width, self.heads, 1, _Format.flag,
                                       C.cast(C.byref(self.arr, i * C.sizeof(L.BlockWeights)), C.POINTER(L.BlockWeights)))
                         for i in range(n)]
 
@@ -121,27 +133,27 @@ class TowerState:
         intermediate the backward needs and the block output."""
         lib, w, D, H, p = L.lib(), self.layers[i], self.width, self.heads, self.p_drop
         rows, dev, st = n_seq * seq_len, x_in.device, L.stream()
-        e16 = lambda r, c: torch.empty(r, c, dtype=BF16, device=dev)
+        e16 = lambda r, c: torch.empty(r, c, dtype=_Format.dtype, device=dev)
         e32 = lambda r, c: torch.empty(r, c, dtype=F32, device=dev)
         a1, qkv, ao, x_mid, a2, u = e16(rows, D), e16(rows, 3 * D), e16(rows, D), e32(rows, D), e16(rows, D), e16(rows, 4 * D)
         L.check(lib.ovmr_layernorm(x_in.data_ptr(), D, rows, D, None, 0, w["ln1_w"].data_ptr(), w["ln1_b"].data_ptr(), None, 0,
-                                   a1.data_ptr(), D, None, None, FP16_FLAG, st), "ovmr_layernorm")
+                                   a1.data_ptr(), D, None, None, _Format.flag, st), "ovmr_layernorm")
         _gemm(a1, D, w["qkv_w"], D, rows, 3 * D, D, qkv, 3 * D, bias=w["qkv_b"], out16=True)
         if p > 0:
-            L.check(lib.ovmr_attention_dropout_forward(qkv.data_ptr(), ao.data_ptr(), n_seq, seq_len, D, H, int(causal), FP16_FLAG,
+            L.check(lib.ovmr_attention_dropout_forward(qkv.data_ptr(), ao.data_ptr(), n_seq, seq_len, D, H, int(causal), _Format.flag,
                                                        p, self._seed(i, 0), st), "ovmr_attention_dropout_forward")
         else:
-            L.check(lib.ovmr_attention(qkv.data_ptr(), ao.data_ptr(), n_seq, seq_len, D, H, int(causal), FP16_FLAG, st), "ovmr_attention")
+            L.check(lib.ovmr_attention(qkv.data_ptr(), ao.data_ptr(), n_seq, seq_len, D, H, int(causal), _Format.flag, st), "ovmr_attention")
         _gemm(ao, D, w["out_w"], D, rows, D, D, x_mid, D, bias=w["out_b"], resid=x_in, ldr=D)
         L.check(lib.ovmr_layernorm(x_mid.data_ptr(), D, rows, D, None, 0, w["ln2_w"].data_ptr(), w["ln2_b"].data_ptr(), None, 0,
-                                   a2.data_ptr(), D, None, None, FP16_FLAG, st), "ovmr_layernorm")
+                                   a2.data_ptr(), D, None, None, _Format.flag, st), "ovmr_layernorm")
         _gemm(a2, D, w["fc_w"], D, rows, 4 * D, D, u, 4 * D, bias=w["fc_b"], out16=True, act=0)
         h = None
         if need_h:
             h = e16(rows, 4 * D)
             _gemm(a2, D, w["fc_w"], D, rows, 4 * D, D, h, 4 * D, bias=w["fc_b"], out16=True, act=1)
             if p > 0:   # dropout2
-                L.check(lib.ovmr_dropout_16(h.data_ptr(), h.data_ptr(), h.numel(), p, self._seed(i, 1), FP16_FLAG, st), "ovmr_dropout_16")
+                L.check(lib.ovmr_dropout_16(h.data_ptr(), h.data_ptr(), h.numel(), p, self._seed(i, 1), _Format.flag, st), "ovmr_dropout_16")
         return a1, qkv, ao, x_mid, a2, u, h
 
     def _block_forward_dropout(self, i: int, x, n_seq, seq_len, causal):
@@ -173,7 +185,7 @@ class TowerState:
     def _block_backward(self, i: int, x_in, n_seq, seq_len, causal, dy, grads: Optional[Dict[str, torch.Tensor]]):
         lib, w, D, H, p = L.lib(), self.layers[i], self.width, self.heads, self.p_drop
         rows, dev, st = n_seq * seq_len, x_in.device, L.stream()
-        e16 = lambda r, c: torch.empty(r, c, dtype=BF16, device=dev)
+        e16 = lambda r, c: torch.empty(r, c, dtype=_Format.dtype, device=dev)
         e32 = lambda r, c: torch.empty(r, c, dtype=F32, device=dev)
         want = grads is not None
         a1, qkv, ao, x_mid, a2, u, h = self._block_internals(i, x_in, n_seq, seq_len, causal, need_h=want)
@@ -188,7 +200,7 @@ class TowerState:
         if p > 0:
             L.check(lib.ovmr_dropout_add(dh.data_ptr(), None, dh.data_ptr(), dh.numel(), p, self._seed(i, 1), st), "ovmr_dropout_add")
         du = e16(rows, 4 * D)
-        L.check(lib.ovmr_quickgelu_backward(u.data_ptr(), dh.data_ptr(), du.data_ptr(), du.numel(), FP16_FLAG, st),
+        L.check(lib.ovmr_quickgelu_backward(u.data_ptr(), dh.data_ptr(), du.data_ptr(), du.numel(), _Format.flag, st),
                 "ovmr_quickgelu_backward")
         da2 = e32(rows, D)
         _gemm(du, 4 * D, w["fc_wT"], 4 * D, rows, D, 4 * D, da2, D)
@@ -202,7 +214,7 @@ class TowerState:
         _gemm(dxm16, D, w["out_wT"], D, rows, D, D, dao, D, out16=True)
         dqkv = e16(rows, 3 * D)
         L.check(lib.ovmr_attention_backward(qkv.data_ptr(), dao.data_ptr(), dqkv.data_ptr(), n_seq, seq_len, D, H, int(causal),
-                                            FP16_FLAG, p, self._seed(i, 0), st), "ovmr_attention_backward")
+                                            _Format.flag, p, self._seed(i, 0), st), "ovmr_attention_backward")
         da1 = e32(rows, D)
         _gemm(dqkv, 3 * D, w["qkv_wT"], 3 * D, rows, D, 3 * D, da1, D)
         dx_in = e32(rows, D)
@@ -238,7 +250,14 @@ class GeneratorTrainer:
     """Loss, gradients and Adam step of the visual token generator of a `CustomCLIP` (native; see module docstring)."""
 
     def __init__(self, custom_clip, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 dropout: Optional[float] = None, seed: int = 0):
+                 dropout: Optional[float] = None, seed: int = 0, fp16: Optional[bool] = None, loss_scale: Optional[float] = None):
+        """fp16: 16-bit format of the training operands; default = the format the text / aggregator towers use at inference
+        (`precision().text_fp16`: IEEE fp16 in the default `mixed` mode), so that the generator is optimised against the
+        text tower it is evaluated with.  fp16 gradients are kept in range by a static loss scale (default 1024; 1 for bf16)."""
+        from .config import precision
+        self.fp16 = precision().text_fp16 if fp16 is None else bool(fp16)
+        self.loss_scale = float(loss_scale) if loss_scale is not None else (1024.0 if self.fp16 else 1.0)
+        _set_format(self.fp16)
         self.m = custom_clip
         self.device = custom_clip.device
         clip_model = custom_clip.text_encoder._clip
@@ -254,8 +273,8 @@ class GeneratorTrainer:
         self.keep = dict(pos=self.text_engine.keep["pos"],
                          lnf_w=clip_model.ln_final.weight.detach().to(dev, F32).contiguous(),
                          lnf_b=clip_model.ln_final.bias.detach().to(dev, F32).contiguous(),
-                         proj_t=clip_model.text_projection.detach().t().to(dev, F32).to(BF16).contiguous(),   # [E, W]
-                         proj=clip_model.text_projection.detach().to(dev, F32).to(BF16).contiguous())        # [W, E]
+                         proj_t=clip_model.text_projection.detach().t().to(dev, F32).to(_Format.dtype).contiguous(),   # [E, W]
+                         proj=clip_model.text_projection.detach().to(dev, F32).to(_Format.dtype).contiguous())        # [W, E]
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.params = dict(pl.named_parameters())
         self.state = {k: (torch.zeros_like(p.data, dtype=F32), torch.zeros_like(p.data, dtype=F32)) for k, p in self.params.items()}
@@ -276,9 +295,9 @@ class GeneratorTrainer:
         saved = self.text.forward_save(x, n, Lq, True)
         idx32 = idx.to(device=dev, dtype=I32).contiguous()
         E_ = self.keep["proj_t"].shape[0]
-        z16 = torch.empty(n, W, dtype=BF16, device=dev)
+        z16 = torch.empty(n, W, dtype=_Format.dtype, device=dev)
         L.check(lib.ovmr_layernorm(x.data_ptr(), W, n, W, idx32.data_ptr(), Lq, self.keep["lnf_w"].data_ptr(),
-                                   self.keep["lnf_b"].data_ptr(), None, 0, z16.data_ptr(), W, None, None, FP16_FLAG, st),
+                                   self.keep["lnf_b"].data_ptr(), None, 0, z16.data_ptr(), W, None, None, _Format.flag, st),
                 "ovmr_layernorm")
         feat = torch.empty(n, E_, dtype=F32, device=dev)
         _gemm(z16, W, self.keep["proj_t"], W, n, E_, W, feat, E_)
@@ -290,6 +309,8 @@ class GeneratorTrainer:
         dlogits = torch.zeros(R, bank.Cpad, dtype=F32, device=dev)
         L.check(lib.ovmr_cross_entropy(logits.data_ptr(), logits.shape[1], train_labels.data_ptr(), R, n, loss.data_ptr(),
                                        dlogits.data_ptr(), bank.Cpad, st), "ovmr_cross_entropy")
+        if self.loss_scale != 1.0:
+            dlogits.mul_(self.loss_scale)     # every gradient downstream carries the scale; removed in loss_and_grads
         # ---- backward: logits -> classifier rows -> projection -> ln_final (gathered rows) -> text tower
         a, rp = _transpose16(dlogits, R, bank.Cpad)                          # [Cpad, Rp]
         b, _ = _transpose16(f_img, R, E_)                                    # [E, Rp]
@@ -309,6 +330,7 @@ class GeneratorTrainer:
     def loss_and_grads(self, image: torch.Tensor, label: torch.Tensor, split_point: Optional[int] = None):
         m, dev, lib, st = self.m, self.device, L.lib(), L.stream()
         pl = m.prompt_learner
+        _set_format(self.fp16)
         self.agg.sync()   # the loss must be evaluated at the CURRENT aggregator weights (torch.optim steps between calls)
         n_ins = m.num_ins
         num_cls = image.shape[0] // n_ins
@@ -346,6 +368,10 @@ class GeneratorTrainer:
         grads: Dict[str, torch.Tensor] = {}
         dagg_in = self.agg.backward(agg_saved, num_cls, T, False, dagg.view(num_cls * T, e), grads)
         grads["cls_token"] = dagg_in.view(num_cls, T, e)[:, :n_ctx].sum(0)
+        if self.loss_scale != 1.0:
+            inv = 1.0 / self.loss_scale
+            for g in grads.values():
+                g.mul_(inv)
         return loss[0], grads
 
     # ------------------------------------------------------------------ MM_CLS_OP.forward_backward

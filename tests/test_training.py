@@ -168,9 +168,10 @@ def test_backward_kernels_match_hand_derived_formulas():
 
 @pytest.mark.gpu
 def test_native_training_step_matches_oracle_autograd():
-    """Loss and all 49 prompt-learner gradients of the native training step (bf16 operands) against torch.autograd on
-    the fp32 oracle (itself pinned to the executed reference): cosine >= 0.99 per tensor, norms within 5 %; the
-    reference-style `loss.backward()` path delivers the same gradients; Adam steps reduce the loss."""
+    """Loss and all 49 prompt-learner gradients of the native training step (fp16 operands + static loss scale: the
+    towers' inference format) against torch.autograd on the fp32 oracle (itself pinned to the executed reference):
+    cosine >= 0.999 per tensor, norms within 1 %, loss within 2e-3; the reference-style `loss.backward()` path delivers
+    the same gradients; Adam steps reduce the loss."""
     from tests.helpers import build_pair
     g, cfg, sd, pl, images, labels, tok, tmpl, n_ins, split = _tiny_problem()
     n_cls = int(g["n_cls"])
@@ -184,12 +185,17 @@ def test_native_training_step_matches_oracle_autograd():
     plr = {k: v.clone().requires_grad_(True) for k, v in pl.items()}
     ref_loss = O.training_loss(sd, plr, tok, tmpl, images, labels, n_ins, split)
     ref = dict(zip(plr, torch.autograd.grad(ref_loss, list(plr.values()))))
-    assert abs(float(loss) - float(ref_loss.detach())) < 2e-2
+    assert tr.fp16 and tr.loss_scale == 1024.0          # the default `mixed` precision trains in the towers' inference format
+    assert abs(float(loss) - float(ref_loss.detach())) < 2e-3
     assert set(grads) == set(ref)
     for k in ref:
         assert grads[k].shape == ref[k].shape, k
-        assert _cos(grads[k], ref[k]) > 0.99, (k, _cos(grads[k], ref[k]))
-        assert abs(float(grads[k].norm()) / float(ref[k].norm()) - 1.0) < 0.05, k
+        assert _cos(grads[k], ref[k]) > 0.999, (k, _cos(grads[k], ref[k]))
+        assert abs(float(grads[k].norm()) / float(ref[k].norm()) - 1.0) < 0.01, k
+    # bf16 operands (OVMR_PRECISION=bf16) remain available at the looser bound they can meet
+    from ovmr_b200.training import GeneratorTrainer
+    _, gb = GeneratorTrainer(model, dropout=0.0, fp16=False).loss_and_grads(images.to(DEV), labels.to(DEV), split_point=split)
+    assert min(_cos(gb[k], ref[k]) for k in ref) > 0.99
     # reference-style flow: model(image, label) -> loss.backward() fills .grad of the prompt learner's parameters
     torch.manual_seed(123)
     out = model(images.to(DEV), labels.to(DEV))
@@ -202,6 +208,38 @@ def test_native_training_step_matches_oracle_autograd():
         last = tr.step(images.to(DEV), labels.to(DEV), split_point=split)
     assert last < first
     model.prompt_learner.eval()
+
+
+@pytest.mark.gpu
+def test_training_step_at_the_reference_batch_vitb16():
+    """ViT-B/16 at the reference's training batch (configs/trainers/MM_CLS_OP/vit_b16_c4_ep50_imagenet21k_pretrain.yaml:
+    1536 images = 192 classes x N_INS 8, split point in [2, 6)): loss and every gradient tensor against torch.autograd on
+    the fp32 oracle run on the GPU (TF32 off) — cosine >= 0.999, norms within 1 %."""
+    from tests.helpers import build_pair
+    from ovmr_b200.clip import tokenize
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n_cls, n_ins, split = 192, 8, 4
+    pair = build_pair("ViT-B/16", n_cls=n_cls, shots=4, device=DEV)
+    model = pair.model
+    model.num_ins = n_ins
+    model.prompt_learner.train()
+    labels = torch.arange(n_cls).repeat_interleave(n_ins)
+    g = torch.Generator().manual_seed(77)
+    base = torch.randn(n_cls, 3, 224, 224, generator=g)
+    images = (base[labels] + 0.5 * torch.randn(n_cls * n_ins, 3, 224, 224, generator=g)).to(DEV)
+    loss, grads = model.trainer(dropout=0.0).loss_and_grads(images, labels.to(DEV), split_point=split)
+    sd = {k: v.to(DEV) for k, v in pair.sd.items()}
+    plr = {k: v.to(DEV).clone().requires_grad_(True) for k, v in pair.pl.items()}
+    ref_loss = O.training_loss(sd, plr, tokenize([f"a class {i}." for i in range(n_cls)]), tokenize("a ."), images,
+                               labels.to(DEV), n_ins, split)
+    ref = dict(zip(plr, torch.autograd.grad(ref_loss, list(plr.values()))))
+    assert abs(float(loss) - float(ref_loss.detach())) < 2e-3
+    for k in ref:
+        assert _cos(grads[k], ref[k]) > 0.999, (k, _cos(grads[k], ref[k]))
+        assert abs(float(grads[k].norm()) / float(ref[k].norm()) - 1.0) < 0.01, k
+    model.prompt_learner.eval()
+    del pair
+    torch.cuda.empty_cache()
 
 
 @pytest.mark.gpu
