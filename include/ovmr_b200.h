@@ -138,6 +138,14 @@ int ovmr_gemm_tn(const void* A, long long lda, const void* B, long long ldb, int
                  const float* bias, const float* resid, long long ldr, void* out, long long ldo,
                  int out_16bit, int act, float alpha, int row_grp, int force_block_n, int fp16, void* stream);
 
+/* The residual GEMMs of a block (attn.out_proj, mlp.c_proj: clip/model.py:191-194) fused with the LayerNorm that follows them
+ * (ln_2 / the next block's ln_1, clip/model.py:153-159): out = resid + A.B^T + bias (fp32, may alias resid) and
+ * ln_out = LayerNorm(out; ln_gamma, ln_beta, eps 1e-5) in the 16-bit format.  N in {512, 768, 1024}. */
+int ovmr_gemm_tn_resid_ln(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                          const float* bias, const float* resid, long long ldr, float* out, long long ldo,
+                          const float* ln_gamma, const float* ln_beta, void* ln_out, long long ld_ln, int fp16,
+                          void* stream);
+
 /* LayerNorm (clip/model.py:153-159), eps 1e-5, fp32 statistics. Source row of output row r is
  * r*gather_mul + (gather ? gather[r] : 0).  Outputs fp32 and/or bf16; optional chained second LN. */
 int ovmr_layernorm(const float* x, long long ldx, int rows, int width, const int* gather, long long gather_mul,

@@ -57,6 +57,8 @@ SIGNATURES = {
                                   c_size_t, c_void_p]),
     "ovmr_gemm_tn": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll,
                              c_void_p, c_ll, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
+    "ovmr_gemm_tn_resid_ln": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p,
+                                      c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "ovmr_layernorm": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll,
                                c_void_p, c_ll, c_void_p, c_void_p, c_int, c_void_p]),
     "ovmr_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

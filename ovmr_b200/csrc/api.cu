@@ -72,6 +72,16 @@ struct Sweep {
   }
 };
 
+// LayerNorm emitted by the residual GEMMs themselves (gemm.cu: row-complete cluster kernel): ln_2 rides on out-proj,
+// the next block's ln_1 on c_proj.  OVMR_FUSE_LN=0 restores the stand-alone LayerNorm kernels (A/B measurements).
+static bool fuse_ln_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("OVMR_FUSE_LN");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
 #define RET_IF(expr)        \
   do {                      \
     int _rc = (expr);       \
@@ -90,10 +100,15 @@ int check_transformer(const ovmr_transformer* t) {
 // One pre-LN residual block on the fp32 residual stream x [rows, D] (clip/model.py:191-194).
 // fold: LayerNorm folding (include/ovmr_b200.h): on entry ws.x16 / ws.stats[0] describe x; emit_next = the block's
 // last GEMM leaves them describing the new x (false for the tower's last block).
+// next: the following block (its ln_1 can be emitted by this block's c_proj), or nullptr.  *next_ln1_done reports whether
+// that happened.
 int run_block(const ovmr_block_weights& bw, float* x, int n_seq, int seq_len, int D, int heads, int causal,
-              int fp16, const TransformerWs& ws, bool ln1_done, bool fold, bool emit_next, Sweep& sw, cudaStream_t st) {
+              int fp16, const TransformerWs& ws, bool ln1_done, bool fold, bool emit_next, Sweep& sw, cudaStream_t st,
+              const ovmr_block_weights* next = nullptr, bool* next_ln1_done = nullptr) {
   const int rows = n_seq * seq_len;
   const int parts = D / 64;
+  const bool fuse = !fold && fuse_ln_enabled() && (D == 512 || D == 768 || D == 1024) && rows >= 4096;
+  if (next_ln1_done) *next_ln1_done = false;
   // x + attn(ln_1(x))
   if (!fold && !ln1_done)
     RET_IF(ovmr::layernorm(x, D, rows, D, nullptr, 0, bw.ln1_w, bw.ln1_b, nullptr, 0, ws.a_bf16, D, nullptr, nullptr, fp16, st,
@@ -111,9 +126,10 @@ int run_block(const ovmr_block_weights& bw, float* x, int n_seq, int seq_len, in
   GemmEpilogue op;
   op.bias = bw.out_b; op.resid = x; op.ldr = D; op.out = x; op.ldo = D; op.out_bf16 = 0; op.fp16 = fp16; op.reverse = sw.next();
   if (fold) { op.out16 = ws.x16; op.ld16 = D; op.stats_out = ws.stats[1]; }
+  if (fuse) { op.ln_out = ws.x16; op.ld_ln = D; op.ln_gamma = bw.ln2_w; op.ln_beta = bw.ln2_b; }   // ln_2(x') rides on out-proj
   RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.out_w, D, rows, D, D, op, st));
   // x + c_proj(QuickGELU(c_fc(ln_2(x))))
-  if (!fold)
+  if (!fold && !fuse)
     RET_IF(ovmr::layernorm(x, D, rows, D, nullptr, 0, bw.ln2_w, bw.ln2_b, nullptr, 0, ws.a_bf16, D, nullptr, nullptr, fp16, st,
                            sw.next()));
   GemmEpilogue fc;
@@ -123,11 +139,15 @@ int run_block(const ovmr_block_weights& bw, float* x, int n_seq, int seq_len, in
     RET_IF(ovmr::gemm_tn(ws.x16, D, bw.fc_wf, D, rows, 4 * D, D, fc, st));
   } else {
     fc.bias = bw.fc_b;
-    RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.fc_w, D, rows, 4 * D, D, fc, st));
+    RET_IF(ovmr::gemm_tn(fuse ? ws.x16 : ws.a_bf16, D, bw.fc_w, D, rows, 4 * D, D, fc, st));
   }
   GemmEpilogue pj;
   pj.bias = bw.proj_b; pj.resid = x; pj.ldr = D; pj.out = x; pj.ldo = D; pj.out_bf16 = 0; pj.fp16 = fp16; pj.reverse = sw.next();
   if (fold && emit_next) { pj.out16 = ws.x16; pj.ld16 = D; pj.stats_out = ws.stats[0]; }
+  if (fuse && next != nullptr) {   // the next block's ln_1(x'') rides on c_proj
+    pj.ln_out = ws.a_bf16; pj.ld_ln = D; pj.ln_gamma = next->ln1_w; pj.ln_beta = next->ln1_b;
+    if (next_ln1_done) *next_ln1_done = true;
+  }
   RET_IF(ovmr::gemm_tn(ws.big_bf16, 4LL * D, bw.proj_w, 4LL * D, rows, D, 4 * D, pj, st));
   return 0;
 }
@@ -154,9 +174,12 @@ int run_transformer(const ovmr_transformer* t, float* x, int n_seq, int seq_len,
   if (fold && !first_ln1_done)   // 16-bit copy + row statistics of the incoming x (identity LayerNorm pass)
     RET_IF(ovmr::layernorm(x, t->width, static_cast<int>(rows), t->width, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, 0,
                            nullptr, nullptr, t->fp16 != 0, st, sw.next(), ws.x16, t->width, ws.stats[0], t->width / 64));
+  bool ln1_done = first_ln1_done;
   for (int l = 0; l < t->layers; ++l) {
-    RET_IF(run_block(t->blocks[l], x, n_seq, seq_len, t->width, t->heads, causal, t->fp16 != 0, ws,
-                     l == 0 && first_ln1_done, fold, l + 1 < t->layers, sw, st));
+    bool next_done = false;
+    RET_IF(run_block(t->blocks[l], x, n_seq, seq_len, t->width, t->heads, causal, t->fp16 != 0, ws, ln1_done, fold,
+                     l + 1 < t->layers, sw, st, l + 1 < t->layers ? &t->blocks[l + 1] : nullptr, &next_done));
+    ln1_done = next_done;
   }
   return 0;
 }
@@ -317,6 +340,16 @@ int ovmr_gemm_tn(const void* A, long long lda, const void* B, long long ldb, int
   ep.bias = bias; ep.resid = resid; ep.ldr = ldr; ep.out = out; ep.ldo = ldo; ep.out_bf16 = out_16bit;
   ep.act = act; ep.alpha = alpha; ep.row_grp = row_grp; ep.fp16 = fp16 != 0;
   return ovmr::gemm_tn(A, lda, B, ldb, M, N, K, ep, S(stream), force_block_n);
+}
+
+int ovmr_gemm_tn_resid_ln(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const float* bias,
+                          const float* resid, long long ldr, float* out, long long ldo, const float* ln_gamma,
+                          const float* ln_beta, void* ln_out, long long ld_ln, int fp16, void* stream) {
+  GemmEpilogue ep;
+  ep.bias = bias; ep.resid = resid; ep.ldr = ldr; ep.out = out; ep.ldo = ldo; ep.out_bf16 = 0; ep.fp16 = fp16 != 0;
+  ep.ln_out = ln_out; ep.ld_ln = ld_ln; ep.ln_gamma = ln_gamma; ep.ln_beta = ln_beta;
+  OVMR_REQUIRE(ln_out != nullptr, "gemm_tn_resid_ln: null ln_out");
+  return ovmr::gemm_tn(A, lda, B, ldb, M, N, K, ep, S(stream));
 }
 
 int ovmr_layernorm(const float* x, long long ldx, int rows, int width, const int* gather, long long gather_mul,

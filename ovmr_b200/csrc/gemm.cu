@@ -667,6 +667,360 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row-complete residual GEMM that also emits LayerNorm of its output (cluster of NT CTA pairs)
+// ---------------------------------------------------------------------------------------------
+// out-proj and c_proj write the fp32 residual stream x' = x + A W^T + b, and the very next kernel of the block is
+// LayerNorm(x') -> 16-bit operand of the next GEMM: a full HBM pass (4D bytes read + 2D written per token) whose only
+// obstacle to fusion is that a row's statistics span all N = D columns while one CTA pair owns 256 of them.  Here the
+// NT = D / 256 pairs that own the N-tiles of one 256-row block form ONE thread-block cluster (6 CTAs for D = 768, 8 for
+// D = 1024):
+//   pass 1  every epilogue warp adds bias + residual to its 32 rows x 128 columns as usual (residual box TMA-loaded, fp32
+//           x' TMA-stored), writes x' BACK into the TMEM accumulator it came from, and keeps a running (mean, M2) of its
+//           128 values per row (Welford per 32-column chunk, Chan's combination across chunks);
+//   exchange each lane stores its row's partial into the statistics array of every CTA of the cluster that holds the same
+//           rows (distributed shared memory, st.shared::cluster) and arrives (release.cluster) on that CTA's mbarrier;
+//   pass 2  once the 2 NT partials of its rows are in, a warp combines them (Chan), reads x' back from TMEM, applies
+//           (x' - mean) * rstd * gamma + beta, packs to 16 bits and TMA-stores the LayerNorm rows.
+// The LayerNorm kernel and its 4D-byte read of x' disappear; the 2D-byte write is the one the LayerNorm kernel made.
+template <int NT>
+struct RowLnCfg {
+  static constexpr int STAGES = 4;
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = 128 * BLOCK_K * 2;           // this CTA's half of the 256-column weight tile
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t STG_BYTES = 8 * 2 * BOX_BYTES;         // per epilogue warp: two 4-KB boxes
+  static constexpr uint32_t STAT_SLOTS = 2 * NT;                   // (pair, column half) partials per row
+  static constexpr uint32_t STAT_BYTES = 2 * STAT_SLOTS * 128 * 8; // two tile parities x slots x 128 rows x float2
+  static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 8 * 16 + 8 * 2 + 16;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + STAT_BYTES + BAR_BYTES + 1024;
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_acquire(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+      "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+      "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                     const __grid_constant__ CUtensorMap tmLN, int M, int N, int K, GemmEpilogue ep) {
+  using Cfg = RowLnCfg<NT>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BLOCK_N = 256;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
+  const uint32_t stg_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t stat_base = stg_base + Cfg::STG_BYTES;
+  const uint32_t bar_base = stat_base + Cfg::STAT_BYTES;
+  auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };                       // used in the pair leader only
+  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };           // per CTA (multicast commit)
+  auto tfull_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + s); };       // per CTA (multicast commit)
+  auto tempty_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + 2 + s); };  // used in the pair leader only
+  const uint32_t rbar_base = bar_base + 8u * (2 * STAGES + 4);                         // 8 warps x 2 residual-load barriers
+  auto stat_bar = [&](uint32_t s) { return rbar_base + 8u * 16 + 8u * s; };            // per tile parity: partials have landed
+  const uint32_t tmem_slot = rbar_base + 8u * 16 + 8u * 2;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 .. 2 NT - 1
+  const uint32_t pair = rank >> 1, half = rank & 1u; // N-tile of this pair, M half of this CTA
+  const uint32_t leader_rank = rank & ~1u;
+  const bool leader = half == 0;
+  const int cluster_id = blockIdx.x / (2 * NT), n_clusters = gridDim.x / (2 * NT);
+  const int row_blocks = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << (2u * pair));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    tma_prefetch_desc(&tmR);
+    tma_prefetch_desc(&tmLN);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 2);    // leader: arrive.expect_tx (own) + remote arrive (peer producer)
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 16);          // one arrive per epilogue warp of both CTAs of the pair
+      mbar_init(stat_bar(s), NT * 8 * 32);   // one arrive per epilogue LANE of every CTA that holds these rows
+    }
+    for (int s = 0; s < 16; ++s) mbar_init(rbar_base + 8u * s, 1);
+    mbar_fence_init();
+  }
+  cluster_sync_all();  // barriers of all CTAs initialised before anyone signals across the cluster
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer (every CTA; whole warp converged, one elected lane issues) =====================
+    uint32_t stage = 0, phase = 0;
+    for (int rb = cluster_id; rb < row_blocks; rb += n_clusters) {
+      const int rbe = ep.reverse ? row_blocks - 1 - rb : rb;
+      const int m0 = rbe * 2 * BLOCK_M + static_cast<int>(half) * BLOCK_M;       // this CTA's 128 rows
+      const int n0 = static_cast<int>(pair) * BLOCK_N + static_cast<int>(half) * (BLOCK_N / 2);   // its half of the weight rows
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
+          tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * BLOCK_K, n0);
+          if (!leader) mbar_arrive_remote(full_bar(stage), leader_rank);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===================== UMMA issuer (pair leaders; whole warp converged, one elected lane issues) ==========
+      const uint32_t idesc = umma_idesc_16b_f32(2 * BLOCK_M, BLOCK_N, ep.fp16);
+      uint32_t stage = 0, phase = 0, iter = 0;
+      for (int rb = cluster_id; rb < row_blocks; rb += n_clusters, ++iter) {
+        const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            const uint64_t a_desc = umma_desc_k_sw128(sa);
+            const uint64_t b_desc = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_16b_ss_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair_mc(empty_bar(stage), pair_mask);          // frees this stage in both CTAs of the pair
+            if (kb == k_blocks - 1) umma_commit_pair_mc(tfull_bar(as), pair_mask);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (every CTA, its 128 rows x the pair's 256 columns) =====================
+    constexpr int HALF_N = BLOCK_N / 2, CHUNKS = HALF_N / 32;
+    const int ew = warp & 3, chalf = (warp - 4) >> 2;
+    EpiCtx cx{0u, stg_base + (warp - 4) * 2 * BOX_BYTES, rbar_base + 16u * (warp - 4), 0u, 0u};
+    const uint32_t my_row = static_cast<uint32_t>(ew * 32 + lane);                 // row inside this CTA's 128
+    const uint32_t my_slot = pair * 2u + static_cast<uint32_t>(chalf);
+    const float inv_n = 1.0f / static_cast<float>(NT * BLOCK_N);
+    uint32_t iter = 0;
+    for (int rb = cluster_id; rb < row_blocks; rb += n_clusters, ++iter) {
+      const int rbe = ep.reverse ? row_blocks - 1 - rb : rb;
+      const int row0 = rbe * 2 * BLOCK_M + static_cast<int>(half) * BLOCK_M + ew * 32;
+      const int col0 = static_cast<int>(pair) * BLOCK_N + chalf * HALF_N;
+      const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
+      const uint32_t taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16) + chalf * HALF_N;
+      const bool rows_live = row0 < M;     // (a warp entirely below the matrix still takes part in the exchange)
+      if (rows_live) resid_issue_load<2>(&tmR, N, row0, col0, cx, lane);
+      {   // residual boxes of this CTA's next row block: into L2 a whole main loop ahead
+        const int nrb = rb + n_clusters;
+        if (nrb < row_blocks && lane == 0) {
+          const int nrbe = ep.reverse ? row_blocks - 1 - nrb : nrb;
+          const int nr = nrbe * 2 * BLOCK_M + static_cast<int>(half) * BLOCK_M + ew * 32;
+          if (nr < M)
+            for (int c = 0; c < CHUNKS; ++c) tma_prefetch_l2_2d(&tmR, col0 + 32 * c, nr);
+        }
+      }
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      // ---------------- pass 1: x' = acc + bias + x -> fp32 out, back into TMEM, running (mean, M2) of this row
+      float run_mean = 0.f, run_m2 = 0.f;
+      if (rows_live) {
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS; ++c) {
+          const int n0 = col0 + 32 * c;
+          uint32_t v[32];
+          tmem_ld32(taddr + 32 * c, v);
+          if (c + 1 < CHUNKS) resid_issue_load<2>(&tmR, N, row0, n0 + 32, cx, lane);
+          tmem_ld_wait();
+          const uint32_t buf = cx.stg + (cx.n_use % 2) * BOX_BYTES;
+          mbar_wait(cx.rbar + 8u * (cx.n_use & 1u), (cx.n_use >> 1) & 1u);  // residual box has landed
+          ++cx.n_use;
+          float csum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int n = n0 + 4 * j;
+            const uint32_t a = buf + lane * 128 + ((j ^ (lane & 7)) << 4);
+            float4 r;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory");
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.bias) b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+            r.x += __uint_as_float(v[4 * j + 0]) + b.x;
+            r.y += __uint_as_float(v[4 * j + 1]) + b.y;
+            r.z += __uint_as_float(v[4 * j + 2]) + b.z;
+            r.w += __uint_as_float(v[4 * j + 3]) + b.w;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r.x), "f"(r.y), "f"(r.z), "f"(r.w) : "memory");
+            v[4 * j + 0] = __float_as_uint(r.x);
+            v[4 * j + 1] = __float_as_uint(r.y);
+            v[4 * j + 2] = __float_as_uint(r.z);
+            v[4 * j + 3] = __float_as_uint(r.w);
+            csum += (r.x + r.y) + (r.z + r.w);
+          }
+          tmem_st32(taddr + 32 * c, v);   // x' back into the accumulator columns it came from (read again in pass 2)
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, buf, n0, row0);
+            tma_store_commit();
+          }
+          // Welford over the chunk, Chan's combination with the running statistics of the chunks before it
+          const float cmean = csum * (1.0f / 32.0f);
+          float cm2 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float d = __uint_as_float(v[e]) - cmean;
+            cm2 = fmaf(d, d, cm2);
+          }
+          const float na = 32.0f * static_cast<float>(c), ntot = na + 32.0f;
+          const float delta = cmean - run_mean;
+          run_mean += delta * (32.0f / ntot);
+          run_m2 += cm2 + delta * delta * (na * 32.0f / ntot);
+        }
+        tmem_st_wait();
+      }
+      // ---------------- exchange: this row's partial to every CTA of the cluster that holds the same rows
+      {
+        const uint32_t slot_addr = stat_base + ((as * Cfg::STAT_SLOTS + my_slot) * 128u + my_row) * 8u;
+#pragma unroll
+        for (uint32_t p = 0; p < static_cast<uint32_t>(NT); ++p) {
+          const uint32_t target = 2u * p + half;
+          st_cluster_f2(mapa_u32(slot_addr, target), run_mean, run_m2);
+          mbar_arrive_cluster_release(mapa_u32(stat_bar(as), target));
+        }
+      }
+      mbar_wait_cluster_acquire(stat_bar(as), aphase);
+      // ---------------- pass 2: LayerNorm of x' from TMEM -> 16-bit rows
+      if (rows_live) {
+        float mean = 0.f, m2 = 0.f;
+        const float2* sp = reinterpret_cast<const float2*>(smem_gen + (stat_base - smem_base)) + (as * Cfg::STAT_SLOTS) * 128u + my_row;
+#pragma unroll
+        for (uint32_t s = 0; s < Cfg::STAT_SLOTS; ++s) {   // Chan: partials of 128 values each
+          const float2 pm = sp[s * 128u];
+          const float na = 128.0f * static_cast<float>(s), ntot = na + 128.0f;
+          const float delta = pm.x - mean;
+          mean += delta * (128.0f / ntot);
+          m2 += pm.y + delta * delta * (na * 128.0f / ntot);
+        }
+        const float rstd = rsqrtf(m2 * inv_n + 1e-5f);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c2 = 0; c2 < CHUNKS / 2; ++c2) {       // 64 columns = one 128-byte row of the 16-bit box
+          const int n0 = col0 + 64 * c2;
+          uint32_t v[64];
+          tmem_ld32(taddr + 64 * c2, v);
+          tmem_ld32(taddr + 64 * c2 + 32, v + 32);
+          tmem_ld_wait();
+          if (c2 == CHUNKS / 2 - 1) {   // everything of this tile is in registers: hand the accumulator stage back to the leader
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tempty_bar(as), leader_rank);
+          }
+          const uint32_t buf = cx.stg + (c2 & 1) * BOX_BYTES;
+          if (lane == 0) tma_store_wait_read<0>();     // every earlier store of this warp has read its box
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int n = n0 + 8 * j;
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + n));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + n + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + n));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + n + 4));
+            float y[8];
+            y[0] = fmaf((__uint_as_float(v[8 * j + 0]) - mean) * rstd, g0.x, b0.x);
+            y[1] = fmaf((__uint_as_float(v[8 * j + 1]) - mean) * rstd, g0.y, b0.y);
+            y[2] = fmaf((__uint_as_float(v[8 * j + 2]) - mean) * rstd, g0.z, b0.z);
+            y[3] = fmaf((__uint_as_float(v[8 * j + 3]) - mean) * rstd, g0.w, b0.w);
+            y[4] = fmaf((__uint_as_float(v[8 * j + 4]) - mean) * rstd, g1.x, b1.x);
+            y[5] = fmaf((__uint_as_float(v[8 * j + 5]) - mean) * rstd, g1.y, b1.y);
+            y[6] = fmaf((__uint_as_float(v[8 * j + 6]) - mean) * rstd, g1.z, b1.z);
+            y[7] = fmaf((__uint_as_float(v[8 * j + 7]) - mean) * rstd, g1.w, b1.w);
+            const uint32_t p0 = pack16x2(y[0], y[1], ep.fp16), p1 = pack16x2(y[2], y[3], ep.fp16);
+            const uint32_t p2 = pack16x2(y[4], y[5], ep.fp16), p3 = pack16x2(y[6], y[7], ep.fp16);
+            const uint32_t dst = buf + lane * 128 + ((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmLN, buf, n0, row0);
+            tma_store_commit();
+          }
+        }
+        if (lane == 0) tma_store_wait_read<0>();   // the boxes are refilled by the next tile's residual loads
+        __syncwarp();
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(tempty_bar(as), leader_rank);
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // all remote arrives / peer smem accesses are done before any CTA of the cluster retires
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
@@ -741,6 +1095,59 @@ int launch_pair(const void* A, long long lda, const void* B, long long ldb, int 
   return 0;
 }
 
+template <int NT>
+int launch_rowln(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                 const GemmEpilogue& ep, cudaStream_t stream) {
+  using Cfg = RowLnCfg<NT>;
+  Maps mp;
+  int rc = build_maps(mp, A, lda, B, ldb, M, N, K, ep, EPI_F32_RESID, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&mp.c16, ep.ln_out, 2, M, N, ep.ld_ln, 32, 64);
+  if (rc) return rc;
+  auto kern = gemm_tn_rowln_kernel<NT>;
+  static PerDeviceOnce attr;
+  static PerDeviceSize max_clusters;   // co-resident clusters of 2 NT CTAs (one CTA per SM) on this device
+  if (attr.first()) {
+    OVMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(2 * NT * 64);
+    q.blockDim = dim3(GEMM_THREADS);
+    q.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2 * NT;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    q.attrs = qa;
+    q.numAttrs = 1;
+    int n = 0;
+    OVMR_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &q));
+    OVMR_REQUIRE(n > 0, "gemm: no cluster of %d CTAs fits this device", 2 * NT);
+    max_clusters.cur() = static_cast<size_t>(n);
+  }
+  const int row_blocks = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int cap = static_cast<int>(max_clusters.cur());
+  const int clusters = row_blocks < cap ? row_blocks : cap;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * NT * clusters);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2 * NT;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl_enabled() && !profiling()) ? 2 : 1;
+  ProfScope prof(PROF_GEMM, 2.0 * M * N * K, stream);
+  OVMR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mp.a, mp.b, mp.c, mp.r, mp.c16, M, N, K, ep));
+  count_launches(1);
+  return 0;
+}
+
 template <int MODE>
 int dispatch_tile(int bn, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                   const GemmEpilogue& ep, cudaStream_t stream) {
@@ -799,6 +1206,16 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, i
                  "gemm: the 16-bit copy + row statistics need the fp32 residual epilogue, N %% 64 == 0 (N=%d) and an aligned out16",
                  N);
     return dispatch_tile<EPI_F32_RESID_EMIT>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+  }
+  if (ep.ln_out != nullptr) {
+    // residual GEMM + LayerNorm of its output rows in one kernel (cluster of N / 256 CTA pairs per 256-row block)
+    OVMR_REQUIRE(tma_resid && ep.ln_gamma != nullptr && ep.ln_beta != nullptr && ep.ld_ln % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(ep.ln_out) & 15) == 0 && (N == 512 || N == 768 || N == 1024),
+                 "gemm: the LayerNorm-emitting residual epilogue needs the TMA residual path, gamma / beta, an aligned "
+                 "16-bit output and N in {512, 768, 1024} (N=%d)", N);
+    if (N == 512) return launch_rowln<2>(A, lda, B, ldb, M, N, K, ep, stream);
+    if (N == 768) return launch_rowln<3>(A, lda, B, ldb, M, N, K, ep, stream);
+    return launch_rowln<4>(A, lda, B, ldb, M, N, K, ep, stream);
   }
   if (tma_resid) return dispatch_tile<EPI_F32_RESID>(bn, A, lda, B, ldb, M, N, K, ep, stream);
   return dispatch_tile<EPI_GENERIC>(bn, A, lda, B, ldb, M, N, K, ep, stream);

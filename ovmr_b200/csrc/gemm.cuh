@@ -41,6 +41,13 @@ struct GemmEpilogue {
   int stats_parts = 0;
   int ln_width = 0;
   const float* colsum = nullptr;
+  // ---- LayerNorm of the OUTPUT rows emitted by the fp32-residual epilogue itself (gemm.cu: row-complete cluster kernel):
+  // ln_out[m, :] = LayerNorm(out[m, :]; ln_gamma, ln_beta, eps 1e-5) in the 16-bit format, leading dim ld_ln.  Needs
+  // N in {512, 768, 1024} (the whole row inside one cluster of N / 256 CTA pairs) and the TMA residual path.
+  void* ln_out = nullptr;
+  long long ld_ln = 0;
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
   int reverse = 0;  // walk the output tiles last-to-first (see api.cu: alternating sweep direction keeps the
                     // rows the previous kernel wrote last — still resident in L2 — first in line)
 };

@@ -139,6 +139,42 @@ def test_attention(n_seq, Lq, heads, causal, fp16):
     assert err < (4e-3 if fp16 else 2e-2), err
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 768, 768), (5000, 768, 3072), (6500, 1024, 1024), (4100, 512, 2048), (100864, 768, 768)])
+@pytest.mark.parametrize("fp16", [0, 1])
+def test_residual_gemm_emitting_layernorm(M, N, K, fp16):
+    """out-proj / c_proj with the following LayerNorm fused (row-complete cluster kernel): the fp32 residual stream must
+    equal the plain residual GEMM's, and the emitted 16-bit rows LayerNorm(out) computed in fp32 (clip/model.py:153-159),
+    including rows whose mean dwarfs their spread (statistics are combined with Chan's formula, not sum / sum of squares)."""
+    L, lib = _lib()
+    t16 = torch.float16 if fp16 else torch.bfloat16
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(t16)
+    B = (torch.randn(N, K, generator=g) * 0.05).to(t16)
+    bias = torch.randn(N, generator=g)
+    resid = torch.randn(M, N, generator=g) * 2.0
+    resid[: min(M, 64)] += 300.0                       # large common offset: mean >> std for these rows
+    gamma = 1.0 + 0.2 * torch.randn(N, generator=g)
+    beta = 0.1 * torch.randn(N, generator=g)
+    dev = lambda t: t.to(DEV).contiguous()
+    Ad, Bd, bd, gd, btd = dev(A), dev(B), dev(bias), dev(gamma), dev(beta)
+    x = dev(resid)
+    ln = torch.zeros(M, N, dtype=t16, device=DEV)
+    L.check(lib.ovmr_gemm_tn_resid_ln(Ad.data_ptr(), K, Bd.data_ptr(), K, M, N, K, bd.data_ptr(), x.data_ptr(), N, x.data_ptr(), N,
+                                      gd.data_ptr(), btd.data_ptr(), ln.data_ptr(), N, fp16, L.stream()))
+    torch.cuda.synchronize()
+    ref_x = resid.to(DEV).double() + Ad.double() @ Bd.double().t() + bd.double()
+    assert (x.double() - ref_x).abs().max() < 2e-3 * max(1.0, float(ref_x.abs().max()) / 300.0)
+    ref_ln = torch.nn.functional.layer_norm(x.float(), (N,), gd, btd, 1e-5)      # LayerNorm of the rows the kernel wrote
+    err = (ln.float() - ref_ln).abs().max().item()
+    assert err < (6e-3 if fp16 else 4e-2), err
+    # second launch in place (x is both residual and output) must not disturb rows of other tiles
+    x2 = dev(resid)
+    L.check(lib.ovmr_gemm_tn(Ad.data_ptr(), K, Bd.data_ptr(), K, M, N, K, bd.data_ptr(), x2.data_ptr(), N, x2.data_ptr(), N, 0, 0,
+                             1.0, 0, 0, fp16, L.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(x, x2), "fp32 residual stream differs from the plain residual GEMM's"
+
+
 def _attention_ref(qkv, n_seq, Lq, heads, causal):
     D = heads * 64
     q, k, v = (t.view(n_seq, Lq, heads, 64).transpose(1, 2) for t in qkv.split(D, dim=-1))
