@@ -145,6 +145,16 @@ int ovmr_gemm_tn_resid_ln(const void* A, long long lda, const void* B, long long
                           const float* bias, const float* resid, long long ldr, float* out, long long ldo,
                           const float* ln_gamma, const float* ln_beta, void* ln_out, long long ld_ln, int fp16,
                           void* stream);
+/* Same, with the row statistics exchanged through a caller-provided global scratch (ovmr_gemm_ln_scratch_bytes(M, N) bytes,
+ * 16-byte aligned, ZEROED once by the caller) instead of distributed shared memory: the kernel then runs on CTA pairs
+ * anywhere on the chip (24 row blocks in flight at N = 768 instead of the 22 six-CTA clusters a B200 can place).
+ * generation = 1, 2, 3, ... for successive launches that share one scratch (same M, same stream); the towers carve the
+ * scratch from their workspace and do this themselves. */
+size_t ovmr_gemm_ln_scratch_bytes(long long M, int N);
+int ovmr_gemm_tn_resid_ln_gx(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                             const float* bias, const float* resid, long long ldr, float* out, long long ldo,
+                             const float* ln_gamma, const float* ln_beta, void* ln_out, long long ld_ln, int fp16,
+                             void* scratch, size_t scratch_bytes, unsigned generation, void* stream);
 
 /* LayerNorm (clip/model.py:153-159), eps 1e-5, fp32 statistics. Source row of output row r is
  * r*gather_mul + (gather ? gather[r] : 0).  Outputs fp32 and/or bf16; optional chained second LN. */

@@ -59,6 +59,9 @@ SIGNATURES = {
                              c_void_p, c_ll, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
     "ovmr_gemm_tn_resid_ln": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p,
                                       c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "ovmr_gemm_ln_scratch_bytes": (c_size_t, [c_ll, c_int]),
+    "ovmr_gemm_tn_resid_ln_gx": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p,
+                                         c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_size_t, C.c_uint, c_void_p]),
     "ovmr_layernorm": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll,
                                c_void_p, c_ll, c_void_p, c_void_p, c_int, c_void_p]),
     "ovmr_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -152,7 +155,7 @@ def launch_count() -> int:
     return int(load().ovmr_launch_count())
 
 
-PROFILE_CLASSES = ("gemm", "attention", "layernorm", "patchify", "head")
+PROFILE_CLASSES = ("gemm", "attention", "layernorm", "patchify", "head", "gemm_ln")
 
 
 def profile_enable(on: bool):

@@ -82,6 +82,23 @@ static bool fuse_ln_enabled() {
   return on;
 }
 
+// Exchange scratch of the LayerNorm-emitting residual GEMMs (gemm.cuh: ln_scratch / ln_gen): carved from the per-row
+// statistics buffers of the workspace (unused unless the tower is LN-folded), counters zeroed once per tower call, one
+// generation per launch.  Measured slower than the cluster / distributed-shared-memory form at D = 768 (out-proj 232 vs 223 us,
+// c_proj 439 vs 418 us at M = 100,864: the L2 round trips of the exchange cost more than the 12 extra SMs bring), so it is
+// opt-in: OVMR_LN_XCHG=global.
+struct LnExchange {
+  void* scratch = nullptr;
+  unsigned gen = 0;
+};
+static bool ln_global_exchange() {
+  static const bool on = [] {
+    const char* e = getenv("OVMR_LN_XCHG");
+    return e != nullptr && e[0] == 'g';
+  }();
+  return on;
+}
+
 #define RET_IF(expr)        \
   do {                      \
     int _rc = (expr);       \
@@ -104,10 +121,14 @@ int check_transformer(const ovmr_transformer* t) {
 // that happened.
 int run_block(const ovmr_block_weights& bw, float* x, int n_seq, int seq_len, int D, int heads, int causal,
               int fp16, const TransformerWs& ws, bool ln1_done, bool fold, bool emit_next, Sweep& sw, cudaStream_t st,
-              const ovmr_block_weights* next = nullptr, bool* next_ln1_done = nullptr) {
+              const ovmr_block_weights* next = nullptr, bool* next_ln1_done = nullptr, LnExchange* lx = nullptr) {
   const int rows = n_seq * seq_len;
   const int parts = D / 64;
-  const bool fuse = !fold && fuse_ln_enabled() && (D == 512 || D == 768 || D == 1024) && rows >= 4096;
+  // D = 1024 (ViT-L) stays on the plain residual GEMM + LayerNorm kernel: a row block needs a cluster of 8 CTAs there, only
+  // 16 of which fit a B200 (128 of 148 SMs); measured at M = 147,712: out-proj 587 (cluster) / 529 (global exchange) against
+  // 303 + 151 us unfused, c_proj 1156 / 1135 against 922 + 143 us (tools/bench_resid_ln.py, profiles/r02_resid_ln.md).
+  static const bool fuse_1024 = [] { const char* e = getenv("OVMR_FUSE_LN_1024"); return e != nullptr && e[0] == '1'; }();
+  const bool fuse = !fold && fuse_ln_enabled() && (D == 512 || D == 768 || (D == 1024 && fuse_1024)) && rows >= 4096;
   if (next_ln1_done) *next_ln1_done = false;
   // x + attn(ln_1(x))
   if (!fold && !ln1_done)
@@ -126,7 +147,10 @@ int run_block(const ovmr_block_weights& bw, float* x, int n_seq, int seq_len, in
   GemmEpilogue op;
   op.bias = bw.out_b; op.resid = x; op.ldr = D; op.out = x; op.ldo = D; op.out_bf16 = 0; op.fp16 = fp16; op.reverse = sw.next();
   if (fold) { op.out16 = ws.x16; op.ld16 = D; op.stats_out = ws.stats[1]; }
-  if (fuse) { op.ln_out = ws.x16; op.ld_ln = D; op.ln_gamma = bw.ln2_w; op.ln_beta = bw.ln2_b; }   // ln_2(x') rides on out-proj
+  if (fuse) {   // ln_2(x') rides on out-proj
+    op.ln_out = ws.x16; op.ld_ln = D; op.ln_gamma = bw.ln2_w; op.ln_beta = bw.ln2_b;
+    if (lx && lx->scratch) { op.ln_scratch = lx->scratch; op.ln_gen = ++lx->gen; }
+  }
   RET_IF(ovmr::gemm_tn(ws.a_bf16, D, bw.out_w, D, rows, D, D, op, st));
   // x + c_proj(QuickGELU(c_fc(ln_2(x))))
   if (!fold && !fuse)
@@ -146,6 +170,7 @@ int run_block(const ovmr_block_weights& bw, float* x, int n_seq, int seq_len, in
   if (fold && emit_next) { pj.out16 = ws.x16; pj.ld16 = D; pj.stats_out = ws.stats[0]; }
   if (fuse && next != nullptr) {   // the next block's ln_1(x'') rides on c_proj
     pj.ln_out = ws.a_bf16; pj.ld_ln = D; pj.ln_gamma = next->ln1_w; pj.ln_beta = next->ln1_b;
+    if (lx && lx->scratch) { pj.ln_scratch = lx->scratch; pj.ln_gen = ++lx->gen; }
     if (next_ln1_done) *next_ln1_done = true;
   }
   RET_IF(ovmr::gemm_tn(ws.big_bf16, 4LL * D, bw.proj_w, 4LL * D, rows, D, 4 * D, pj, st));
@@ -175,10 +200,17 @@ int run_transformer(const ovmr_transformer* t, float* x, int n_seq, int seq_len,
     RET_IF(ovmr::layernorm(x, t->width, static_cast<int>(rows), t->width, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, 0,
                            nullptr, nullptr, t->fp16 != 0, st, sw.next(), ws.x16, t->width, ws.stats[0], t->width / 64));
   bool ln1_done = first_ln1_done;
+  LnExchange lx;
+  if (!fold && fuse_ln_enabled() && ln_global_exchange() && rows >= 4096 &&
+      ovmr::gemm_ln_scratch_bytes(rows, t->width) <= 2 * align256(static_cast<size_t>(rows) * (t->width / 64) * sizeof(float2))) {
+    lx.scratch = ws.stats[0];   // stats[0] and stats[1] are contiguous
+    OVMR_CHECK_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(lx.scratch) + ovmr::gemm_ln_scratch_counter_offset(rows, t->width), 0,
+                                    ovmr::gemm_ln_scratch_counter_bytes(rows), st));
+  }
   for (int l = 0; l < t->layers; ++l) {
     bool next_done = false;
     RET_IF(run_block(t->blocks[l], x, n_seq, seq_len, t->width, t->heads, causal, t->fp16 != 0, ws, ln1_done, fold,
-                     l + 1 < t->layers, sw, st, l + 1 < t->layers ? &t->blocks[l + 1] : nullptr, &next_done));
+                     l + 1 < t->layers, sw, st, l + 1 < t->layers ? &t->blocks[l + 1] : nullptr, &next_done, &lx));
     ln1_done = next_done;
   }
   return 0;
@@ -349,6 +381,22 @@ int ovmr_gemm_tn_resid_ln(const void* A, long long lda, const void* B, long long
   ep.bias = bias; ep.resid = resid; ep.ldr = ldr; ep.out = out; ep.ldo = ldo; ep.out_bf16 = 0; ep.fp16 = fp16 != 0;
   ep.ln_out = ln_out; ep.ld_ln = ld_ln; ep.ln_gamma = ln_gamma; ep.ln_beta = ln_beta;
   OVMR_REQUIRE(ln_out != nullptr, "gemm_tn_resid_ln: null ln_out");
+  return ovmr::gemm_tn(A, lda, B, ldb, M, N, K, ep, S(stream));
+}
+
+size_t ovmr_gemm_ln_scratch_bytes(long long M, int N) { return M > 0 && N > 0 ? ovmr::gemm_ln_scratch_bytes(M, N) : 0; }
+
+int ovmr_gemm_tn_resid_ln_gx(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const float* bias,
+                             const float* resid, long long ldr, float* out, long long ldo, const float* ln_gamma,
+                             const float* ln_beta, void* ln_out, long long ld_ln, int fp16, void* scratch, size_t scratch_bytes,
+                             unsigned generation, void* stream) {
+  GemmEpilogue ep;
+  ep.bias = bias; ep.resid = resid; ep.ldr = ldr; ep.out = out; ep.ldo = ldo; ep.out_bf16 = 0; ep.fp16 = fp16 != 0;
+  ep.ln_out = ln_out; ep.ld_ln = ld_ln; ep.ln_gamma = ln_gamma; ep.ln_beta = ln_beta;
+  OVMR_REQUIRE(ln_out != nullptr, "gemm_tn_resid_ln_gx: null ln_out");
+  OVMR_REQUIRE(scratch != nullptr && M > 0 && N > 0 && scratch_bytes >= ovmr::gemm_ln_scratch_bytes(M, N),
+               "gemm_tn_resid_ln_gx: scratch too small (%zu bytes)", scratch_bytes);
+  ep.ln_scratch = scratch; ep.ln_gen = generation;
   return ovmr::gemm_tn(A, lda, B, ldb, M, N, K, ep, S(stream));
 }
 

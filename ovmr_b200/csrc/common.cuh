@@ -49,7 +49,8 @@ struct PerDeviceSize {
 };
 
 // kernel classes for the optional device-side timing (see runtime.cu)
-enum ProfCat { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_ROWOPS = 3, PROF_HEAD = 4, PROF_NCAT = 5 };
+enum ProfCat { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_ROWOPS = 3, PROF_HEAD = 4, PROF_GEMM_LN = 5,
+               PROF_NCAT = 6 };   // PROF_GEMM_LN: residual GEMM + LayerNorm of its output rows in one kernel
 bool profiling();
 void prof_begin(int cat, double work, cudaStream_t s);
 void prof_end(cudaStream_t s);

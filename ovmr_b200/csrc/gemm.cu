@@ -736,7 +736,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
       : "memory");
 }
 
-template <int NT>
+// GX = false: the 2 NT CTAs of a row block are ONE hardware cluster, partials travel through distributed shared memory.
+// GX = true : hardware clusters are the CTA pairs only; the NT pairs of a row block ("group") are consecutive pairs of a
+//             persistent grid whose CTAs are all co-resident, and the partials travel through a global (L2) scratch with
+//             release / acquire counters.  A cluster of 6 (8) CTAs must sit inside one GPC, so only 22 (16) of them fit a
+//             B200 (132 / 128 of 148 SMs); pairs fit everywhere: 24 (18) groups, 144 SMs.
+template <int NT, bool GX>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -763,14 +768,15 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();          // 0 .. 2 NT - 1
-  const uint32_t pair = rank >> 1, half = rank & 1u; // N-tile of this pair, M half of this CTA
+  const uint32_t rank = cluster_ctarank();          // 0 .. 2 NT - 1 (GX: 0 .. 1)
+  // N-tile of this pair, M half of this CTA
+  const uint32_t pair = GX ? (blockIdx.x >> 1) % static_cast<uint32_t>(NT) : rank >> 1, half = rank & 1u;
   const uint32_t leader_rank = rank & ~1u;
   const bool leader = half == 0;
-  const int cluster_id = blockIdx.x / (2 * NT), n_clusters = gridDim.x / (2 * NT);
+  const int cluster_id = blockIdx.x / (2 * NT), n_clusters = gridDim.x / (2 * NT);   // (GX: group of NT consecutive pairs)
   const int row_blocks = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
-  const uint16_t pair_mask = static_cast<uint16_t>(3u << (2u * pair));
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << (2u * (rank >> 1)));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -935,7 +941,32 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tmem_st_wait();
       }
       // ---------------- exchange: this row's partial to every CTA of the cluster that holds the same rows
-      {
+      const long long m_pad = static_cast<long long>(row_blocks) * 2 * BLOCK_M;
+      const float2* gpart = reinterpret_cast<const float2*>(ep.ln_scratch) + (row0 + lane);   // + slot * m_pad
+      if (GX) {
+        // global exchange: partial -> scratch[slot][row] (coalesced), one release-arrive per warp on the counter of
+        // (row block, M half, lane quarter), then wait until all 2 NT warps that hold these rows have arrived.  Warps
+        // entirely below the matrix have no partners and skip both.
+        if (rows_live) {
+          float2* part = reinterpret_cast<float2*>(ep.ln_scratch);
+          uint32_t* cnt = reinterpret_cast<uint32_t*>(part + Cfg::STAT_SLOTS * m_pad) + ((rbe * 2 + static_cast<int>(half)) * 4 + ew);
+          part[my_slot * m_pad + row0 + lane] = make_float2(run_mean, run_m2);
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(1u) : "memory");
+            const uint32_t want = ep.ln_gen * Cfg::STAT_SLOTS;
+            const long long t0 = clock64();
+            while (true) {
+              uint32_t have;
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(cnt) : "memory");
+              if (have >= want) break;
+              if (clock64() - t0 > 8000000000LL) __trap();
+            }
+          }
+          __syncwarp();
+        }
+      } else {
         const uint32_t slot_addr = stat_base + ((as * Cfg::STAT_SLOTS + my_slot) * 128u + my_row) * 8u;
 #pragma unroll
         for (uint32_t p = 0; p < static_cast<uint32_t>(NT); ++p) {
@@ -943,15 +974,15 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           st_cluster_f2(mapa_u32(slot_addr, target), run_mean, run_m2);
           mbar_arrive_cluster_release(mapa_u32(stat_bar(as), target));
         }
+        mbar_wait_cluster_acquire(stat_bar(as), aphase);
       }
-      mbar_wait_cluster_acquire(stat_bar(as), aphase);
       // ---------------- pass 2: LayerNorm of x' from TMEM -> 16-bit rows
       if (rows_live) {
         float mean = 0.f, m2 = 0.f;
         const float2* sp = reinterpret_cast<const float2*>(smem_gen + (stat_base - smem_base)) + (as * Cfg::STAT_SLOTS) * 128u + my_row;
 #pragma unroll
         for (uint32_t s = 0; s < Cfg::STAT_SLOTS; ++s) {   // Chan: partials of 128 values each
-          const float2 pm = sp[s * 128u];
+          const float2 pm = GX ? __ldcg(gpart + s * m_pad) : sp[s * 128u];
           const float na = 128.0f * static_cast<float>(s), ntot = na + 128.0f;
           const float delta = pm.x - mean;
           mean += delta * (128.0f / ntot);
@@ -1095,54 +1126,56 @@ int launch_pair(const void* A, long long lda, const void* B, long long ldb, int 
   return 0;
 }
 
-template <int NT>
+template <int NT, bool GX>
 int launch_rowln(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                  const GemmEpilogue& ep, cudaStream_t stream) {
   using Cfg = RowLnCfg<NT>;
+  constexpr int CLUSTER = GX ? 2 : 2 * NT;   // hardware cluster: the CTA pair (global exchange) or the whole row block
   Maps mp;
   int rc = build_maps(mp, A, lda, B, ldb, M, N, K, ep, EPI_F32_RESID, 128);
   if (rc) return rc;
   rc = make_tmap_2d(&mp.c16, ep.ln_out, 2, M, N, ep.ld_ln, 32, 64);
   if (rc) return rc;
-  auto kern = gemm_tn_rowln_kernel<NT>;
+  auto kern = gemm_tn_rowln_kernel<NT, GX>;
   static PerDeviceOnce attr;
-  static PerDeviceSize max_clusters;   // co-resident clusters of 2 NT CTAs (one CTA per SM) on this device
+  static PerDeviceSize max_groups;   // co-resident row-block groups of 2 NT CTAs (one CTA per SM) on this device
   if (attr.first()) {
     OVMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     cudaLaunchConfig_t q = {};
-    q.gridDim = dim3(2 * NT * 64);
+    q.gridDim = dim3(CLUSTER * 64);
     q.blockDim = dim3(GEMM_THREADS);
     q.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension;
-    qa[0].val.clusterDim.x = 2 * NT;
+    qa[0].val.clusterDim.x = CLUSTER;
     qa[0].val.clusterDim.y = 1;
     qa[0].val.clusterDim.z = 1;
     q.attrs = qa;
     q.numAttrs = 1;
     int n = 0;
     OVMR_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &q));
-    OVMR_REQUIRE(n > 0, "gemm: no cluster of %d CTAs fits this device", 2 * NT);
-    max_clusters.cur() = static_cast<size_t>(n);
+    if (GX) n /= NT;   // NT pairs per group; every CTA of the grid must be resident (the groups wait for each other's partials)
+    OVMR_REQUIRE(n > 0, "gemm: no group of %d CTAs fits this device", 2 * NT);
+    max_groups.cur() = static_cast<size_t>(n);
   }
   const int row_blocks = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-  const int cap = static_cast<int>(max_clusters.cur());
-  const int clusters = row_blocks < cap ? row_blocks : cap;
+  const int cap = static_cast<int>(max_groups.cur());
+  const int groups = row_blocks < cap ? row_blocks : cap;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * NT * clusters);
+  cfg.gridDim = dim3(2 * NT * groups);
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2 * NT;
+  at[0].val.clusterDim.x = CLUSTER;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = (pdl_enabled() && !profiling()) ? 2 : 1;
-  ProfScope prof(PROF_GEMM, 2.0 * M * N * K, stream);
+  ProfScope prof(PROF_GEMM_LN, 2.0 * M * N * K, stream);
   OVMR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mp.a, mp.b, mp.c, mp.r, mp.c16, M, N, K, ep));
   count_launches(1);
   return 0;
@@ -1157,6 +1190,17 @@ int dispatch_tile(int bn, const void* A, long long lda, const void* B, long long
 }
 
 }  // namespace
+
+size_t gemm_ln_scratch_counter_offset(long long M, int N) {
+  const long long m_pad = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (2 * BLOCK_M);
+  return static_cast<size_t>(N / 128) * static_cast<size_t>(m_pad) * sizeof(float2);
+}
+size_t gemm_ln_scratch_counter_bytes(long long M) {
+  return static_cast<size_t>((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * 8 * sizeof(uint32_t);
+}
+size_t gemm_ln_scratch_bytes(long long M, int N) {
+  return gemm_ln_scratch_counter_offset(M, N) + gemm_ln_scratch_counter_bytes(M);
+}
 
 int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
             const GemmEpilogue& ep, cudaStream_t stream, int force_block_n) {
@@ -1213,9 +1257,16 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, i
                      (reinterpret_cast<uintptr_t>(ep.ln_out) & 15) == 0 && (N == 512 || N == 768 || N == 1024),
                  "gemm: the LayerNorm-emitting residual epilogue needs the TMA residual path, gamma / beta, an aligned "
                  "16-bit output and N in {512, 768, 1024} (N=%d)", N);
-    if (N == 512) return launch_rowln<2>(A, lda, B, ldb, M, N, K, ep, stream);
-    if (N == 768) return launch_rowln<3>(A, lda, B, ldb, M, N, K, ep, stream);
-    return launch_rowln<4>(A, lda, B, ldb, M, N, K, ep, stream);
+    if (ep.ln_scratch != nullptr) {
+      OVMR_REQUIRE((reinterpret_cast<uintptr_t>(ep.ln_scratch) & 15) == 0 && ep.ln_gen > 0 && ep.ln_gen < (1u << 24),
+                   "gemm: the global LayerNorm exchange needs an aligned scratch and a generation in [1, 2^24)");
+      if (N == 512) return launch_rowln<2, true>(A, lda, B, ldb, M, N, K, ep, stream);
+      if (N == 768) return launch_rowln<3, true>(A, lda, B, ldb, M, N, K, ep, stream);
+      return launch_rowln<4, true>(A, lda, B, ldb, M, N, K, ep, stream);
+    }
+    if (N == 512) return launch_rowln<2, false>(A, lda, B, ldb, M, N, K, ep, stream);
+    if (N == 768) return launch_rowln<3, false>(A, lda, B, ldb, M, N, K, ep, stream);
+    return launch_rowln<4, false>(A, lda, B, ldb, M, N, K, ep, stream);
   }
   if (tma_resid) return dispatch_tile<EPI_F32_RESID>(bn, A, lda, B, ldb, M, N, K, ep, stream);
   return dispatch_tile<EPI_GENERIC>(bn, A, lda, B, ldb, M, N, K, ep, stream);

@@ -48,6 +48,13 @@ struct GemmEpilogue {
   long long ld_ln = 0;
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;
+  // Optional global exchange scratch for that kernel (gemm_ln_scratch_bytes(M, N) bytes, 16-byte aligned; its counter
+  // tail — gemm_ln_scratch_counter_offset / _bytes — zeroed once, then ln_gen = 1, 2, 3, ... for successive launches with
+  // the same M on the same stream).  With it the row statistics travel through L2 instead of distributed shared memory
+  // and the kernel is no longer bound to clusters of N / 128 CTAs (24 instead of 22 row blocks in flight at N = 768,
+  // 18 instead of 16 at N = 1024 on a B200).  nullptr: the cluster / DSMEM form.
+  void* ln_scratch = nullptr;
+  unsigned ln_gen = 0;
   int reverse = 0;  // walk the output tiles last-to-first (see api.cu: alternating sweep direction keeps the
                     // rows the previous kernel wrote last — still resident in L2 — first in line)
 };
@@ -55,6 +62,12 @@ struct GemmEpilogue {
 // A: 16-bit [M,K] leading dim lda (elements); B: 16-bit [N,K] leading dim ldb (format: ep.fp16).
 // Requirements: K % 8 == 0, N % 8 == 0, lda/ldb % 8 == 0, 16-byte aligned bases.
 // force_block_n: 0 = heuristic, 128 / 256 = 1-CTA kernel with that tile width, 512 = CTA-pair (2-SM) kernel.
+// Scratch of the LayerNorm-emitting residual GEMM's global exchange: [N/128 slots][Mpad] float2 partials followed by
+// Mpad/256 x 8 uint32 arrival counters (Mpad = M rounded up to 256).
+size_t gemm_ln_scratch_bytes(long long M, int N);
+size_t gemm_ln_scratch_counter_offset(long long M, int N);
+size_t gemm_ln_scratch_counter_bytes(long long M);
+
 int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                  const GemmEpilogue& ep, cudaStream_t stream, int force_block_n = 0);
 

@@ -108,6 +108,31 @@ PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   return fn;
 }
 
+// Descriptor cache.  A CUtensorMap is a pure function of (base, extents, strides, box, element size): towers call the
+// same GEMMs on the same workspace pointers batch after batch, so the 5 host-side encodes per GEMM launch (7,500 launches
+// per config-2 step, ~60 per training block) collapse to one lookup each.  Direct-mapped, per thread, no invalidation
+// needed (nothing about the allocation behind `base` is baked into the descriptor).
+struct TmapKey {
+  const void* base;
+  long long d0, d1, d2, s1, s2;
+  int box_rows, box_cols, elem, rank;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 &&
+           box_rows == o.box_rows && box_cols == o.box_cols && elem == o.elem && rank == o.rank;
+  }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool valid; };
+constexpr int kTmapSlots = 1024;
+TmapSlot* tmap_slot(const TmapKey& k) {
+  thread_local std::vector<TmapSlot> slots(kTmapSlots, TmapSlot{{}, {}, false});
+  unsigned long long h = reinterpret_cast<unsigned long long>(k.base) * 0x9E3779B97F4A7C15ull;
+  h ^= static_cast<unsigned long long>(k.d0) * 0xC2B2AE3D27D4EB4Full + static_cast<unsigned long long>(k.d1) * 0x165667B19E3779F9ull;
+  h ^= static_cast<unsigned long long>(k.s1) * 0x27D4EB2F165667C5ull + static_cast<unsigned long long>(k.d2 * 31 + k.s2);
+  h ^= static_cast<unsigned long long>(k.box_rows * 131 + k.box_cols * 7 + k.elem * 3 + k.rank);
+  h ^= h >> 29;
+  return &slots[h & (kTmapSlots - 1)];
+}
+
 }  // namespace
 
 // Row-major [rows, cols] matrix (cols contiguous, leading dim ld elements) -> TMA boxes of box_rows x box_cols
@@ -123,6 +148,12 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, long long r
     set_last_error("make_tmap_2d: box inner extent must be 128 bytes (box_cols=%d elem_bytes=%d)", box_cols, elem_bytes);
     return OVMR_ERR_INVALID;
   }
+  const TmapKey key{base, cols, rows, 0, ld, 0, box_rows, box_cols, elem_bytes, 2};
+  TmapSlot* slot = tmap_slot(key);
+  if (slot->valid && slot->key == key) {
+    *map = slot->map;
+    return 0;
+  }
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
@@ -136,6 +167,7 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, long long r
                    rows, cols, ld, box_rows, box_cols, elem_bytes);
     return OVMR_ERR_INVALID;
   }
+  *slot = TmapSlot{key, *map, true};
   return 0;
 }
 
@@ -145,6 +177,12 @@ int make_tmap_3d_16b(CUtensorMap* map, const void* base, long long d0, long long
   if (!enc) {
     set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
     return OVMR_ERR_INVALID;
+  }
+  const TmapKey key{base, d0, d1, d2, stride1, stride2, box_rows, 64, 2, 3};
+  TmapSlot* slot = tmap_slot(key);
+  if (slot->valid && slot->key == key) {
+    *map = slot->map;
+    return 0;
   }
   cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
   cuuint64_t gstride[2] = {static_cast<cuuint64_t>(stride1) * 2, static_cast<cuuint64_t>(stride2) * 2};
@@ -157,6 +195,7 @@ int make_tmap_3d_16b(CUtensorMap* map, const void* base, long long d0, long long
     set_last_error("cuTensorMapEncodeTiled (3d) failed (%d) base=%p dims=%lld x %lld x %lld", (int)r, base, d0, d1, d2);
     return OVMR_ERR_INVALID;
   }
+  *slot = TmapSlot{key, *map, true};
   return 0;
 }
 

@@ -141,10 +141,13 @@ def test_attention(n_seq, Lq, heads, causal, fp16):
 
 @pytest.mark.parametrize("M,N,K", [(300, 768, 768), (5000, 768, 3072), (6500, 1024, 1024), (4100, 512, 2048), (100864, 768, 768)])
 @pytest.mark.parametrize("fp16", [0, 1])
-def test_residual_gemm_emitting_layernorm(M, N, K, fp16):
-    """out-proj / c_proj with the following LayerNorm fused (row-complete cluster kernel): the fp32 residual stream must
-    equal the plain residual GEMM's, and the emitted 16-bit rows LayerNorm(out) computed in fp32 (clip/model.py:153-159),
-    including rows whose mean dwarfs their spread (statistics are combined with Chan's formula, not sum / sum of squares)."""
+@pytest.mark.parametrize("exchange", ["cluster", "global"])
+def test_residual_gemm_emitting_layernorm(M, N, K, fp16, exchange):
+    """out-proj / c_proj with the following LayerNorm fused (row-complete kernel; row statistics exchanged through
+    distributed shared memory inside a cluster, or through a global scratch between free-standing CTA pairs): the fp32
+    residual stream must equal the plain residual GEMM's, and the emitted 16-bit rows LayerNorm(out) computed in fp32
+    (clip/model.py:153-159), including rows whose mean dwarfs their spread (statistics are combined with Chan's formula,
+    not sum / sum of squares).  The global form is launched three times on one scratch (generations 1, 2, 3)."""
     L, lib = _lib()
     t16 = torch.float16 if fp16 else torch.bfloat16
     g = torch.Generator().manual_seed(M + N + K)
@@ -159,8 +162,18 @@ def test_residual_gemm_emitting_layernorm(M, N, K, fp16):
     Ad, Bd, bd, gd, btd = dev(A), dev(B), dev(bias), dev(gamma), dev(beta)
     x = dev(resid)
     ln = torch.zeros(M, N, dtype=t16, device=DEV)
-    L.check(lib.ovmr_gemm_tn_resid_ln(Ad.data_ptr(), K, Bd.data_ptr(), K, M, N, K, bd.data_ptr(), x.data_ptr(), N, x.data_ptr(), N,
-                                      gd.data_ptr(), btd.data_ptr(), ln.data_ptr(), N, fp16, L.stream()))
+    if exchange == "cluster":
+        L.check(lib.ovmr_gemm_tn_resid_ln(Ad.data_ptr(), K, Bd.data_ptr(), K, M, N, K, bd.data_ptr(), x.data_ptr(), N, x.data_ptr(), N,
+                                          gd.data_ptr(), btd.data_ptr(), ln.data_ptr(), N, fp16, L.stream()))
+    else:
+        nbytes = lib.ovmr_gemm_ln_scratch_bytes(M, N)
+        scratch = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+        for gen in (1, 2, 3):    # the last launch is the one checked; earlier ones ran on other inputs
+            xin = dev(resid) if gen == 3 else dev(resid * 0.5 + gen)
+            x = xin
+            L.check(lib.ovmr_gemm_tn_resid_ln_gx(Ad.data_ptr(), K, Bd.data_ptr(), K, M, N, K, bd.data_ptr(), x.data_ptr(), N,
+                                                 x.data_ptr(), N, gd.data_ptr(), btd.data_ptr(), ln.data_ptr(), N, fp16,
+                                                 scratch.data_ptr(), nbytes, gen, L.stream()))
     torch.cuda.synchronize()
     ref_x = resid.to(DEV).double() + Ad.double() @ Bd.double().t() + bd.double()
     assert (x.double() - ref_x).abs().max() < 2e-3 * max(1.0, float(ref_x.abs().max()) / 300.0)
