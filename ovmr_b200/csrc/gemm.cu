@@ -35,6 +35,9 @@
 // of the previous kernel.  `ep.reverse` walks the tiles last-to-first (alternating sweep direction, api.cu).
 #include "gemm.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace ovmr {
@@ -56,6 +59,17 @@ __device__ __forceinline__ float quick_gelu(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
+}
+
+// L2 prefetch of the A operand `dist` K blocks ahead of the load just issued (0 = off).  The smem ring keeps STAGES x 32 KB
+// per CTA in flight — enough for operands that sit in L2, not for an A operand streamed from HBM (c_proj: the 620 MB MLP
+// hidden, out-proj: the attention output): its main loop ran at 715 cycles per K block against 512 at full MMA rate
+// (profiles/r02_rowln_trace.md).  Past the end of the tile's K loop the prefetch moves on to the next tile's rows.
+__device__ __forceinline__ void prefetch_a_ahead(const CUtensorMap* tmA, int dist, int kb, int k_blocks, int m0, int m0_next) {
+  if (dist <= 0) return;
+  const int kp = kb + dist;
+  if (kp < k_blocks) tma_prefetch_l2_2d(tmA, kp * BLOCK_K, m0);
+  else if (m0_next >= 0 && kp - k_blocks < k_blocks) tma_prefetch_l2_2d(tmA, (kp - k_blocks) * BLOCK_K, m0_next);
 }
 
 // per-warp epilogue bookkeeping
@@ -598,6 +612,10 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m_pair = te / n_tiles, n_blk = te % n_tiles;
       const int m0 = m_pair * 2 * BLOCK_M + rank * BLOCK_M;        // this CTA's 128 rows of the 256-row tile
       const int n0 = n_blk * BLOCK_N + rank * (BLOCK_N / 2);       // this CTA's half of the weight rows
+      // A rows of this CTA's NEXT tile (L2 prefetch past the end of this tile's K loop)
+      const int tnext = tile + n_clusters;
+      const int tne = ep.reverse ? total_tiles - 1 - tnext : tnext;
+      const int m0_next = tnext < total_tiles ? (tne / n_tiles) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M : -1;
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         if (elect_one()) {
@@ -606,6 +624,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
           tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * BLOCK_K, n0);
           if (!leader) mbar_arrive_remote(full_bar(stage), 0);
+          prefetch_a_ahead(&tmA, ep.a_prefetch, kb, k_blocks, m0, m0_next);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -683,18 +702,37 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //   pass 2  once the 2 NT partials of its rows are in, a warp combines them (Chan), reads x' back from TMEM, applies
 //           (x' - mean) * rstd * gamma + beta, packs to 16 bits and TMA-stores the LayerNorm rows.
 // The LayerNorm kernel and its 4D-byte read of x' disappear; the 2D-byte write is the one the LayerNorm kernel made.
-template <int NT>
+// SB staging boxes per epilogue warp (2 or 3) and the smem ring that goes with them.  A warp's pass 1 is a chain of residual
+// boxes (TMA load -> add in place -> TMA store): with two boxes the load of chunk c + 1 can only be issued once the store of
+// chunk c - 1 has been read out, and its ~2000 cycles of latency are exposed on every chunk (profiles/r02_rowln_trace.md:
+// ~2000 cycles per chunk against ~500 of instructions).  With three boxes the first three chunks of a tile are requested
+// before the accumulator is even ready.  The third box costs one main-loop stage: used for K <= 1024 (out-proj: 12-16
+// K blocks per tile, epilogue-bound), not for c_proj (K = 4 D, main-loop-bound).
+template <int NT, int SB>
 struct RowLnCfg {
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = SB == 3 ? 3 : 4;
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = 128 * BLOCK_K * 2;           // this CTA's half of the 256-column weight tile
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t STG_BYTES = 8 * 2 * BOX_BYTES;         // per epilogue warp: two 4-KB boxes
+  static constexpr uint32_t STG_BYTES = 8 * SB * BOX_BYTES;        // per epilogue warp: SB 4-KB boxes
   static constexpr uint32_t STAT_SLOTS = 2 * NT;                   // (pair, column half) partials per row
   static constexpr uint32_t STAT_BYTES = 2 * STAT_SLOTS * 128 * 8; // two tile parities x slots x 128 rows x float2
-  static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 8 * 16 + 8 * 2 + 16;
+  static constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 8 * 4 * 8 + 8 * 2 + 16;
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + STAT_BYTES + BAR_BYTES + 1024;
+  static_assert(SB == 2 || SB == 3, "2 or 3 staging boxes per epilogue warp");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
+
+// residual box of one 32-column chunk -> staging box n_load % SB (its own mbarrier; the box must be free)
+template <int SB>
+__device__ __forceinline__ void rowln_issue_resid(const CUtensorMap* tmR, int row0, int n0, EpiCtx& cx, int lane) {
+  if (lane == 0) {
+    const uint32_t box = cx.n_load % SB;
+    mbar_arrive_expect_tx(cx.rbar + 8u * box, BOX_BYTES);
+    tma_load_2d(cx.stg + box * BOX_BYTES, tmR, cx.rbar + 8u * box, n0, row0);
+  }
+  ++cx.n_load;
+}
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
   uint32_t r;
@@ -736,17 +774,30 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
       : "memory");
 }
 
+// Optional per-phase clock64 trace of CTA 0 (build/rowln_trace, csrc/rowln_trace.cu): -DOVMR_ROWLN_TRACE only.
+#ifdef OVMR_ROWLN_TRACE
+constexpr int RT_TILES = 6, RT_FIRST = 4, RT_EVENTS = 16;
+__device__ long long g_rowln_trace[3][RT_TILES][RT_EVENTS];   // [epilogue warp 4 | epilogue warp 11 | issuer][tile][event]
+#define RTRACE(slot, tile_idx, ev)                                                                                \
+  do {                                                                                                            \
+    if (blockIdx.x == 0 && lane == 0 && (tile_idx) >= RT_FIRST && (tile_idx) < RT_FIRST + RT_TILES)               \
+      g_rowln_trace[slot][(tile_idx) - RT_FIRST][ev] = clock64();                                                 \
+  } while (0)
+#else
+#define RTRACE(slot, tile_idx, ev) do { } while (0)
+#endif
+
 // GX = false: the 2 NT CTAs of a row block are ONE hardware cluster, partials travel through distributed shared memory.
 // GX = true : hardware clusters are the CTA pairs only; the NT pairs of a row block ("group") are consecutive pairs of a
 //             persistent grid whose CTAs are all co-resident, and the partials travel through a global (L2) scratch with
 //             release / acquire counters.  A cluster of 6 (8) CTAs must sit inside one GPC, so only 22 (16) of them fit a
 //             B200 (132 / 128 of 148 SMs); pairs fit everywhere: 24 (18) groups, 144 SMs.
-template <int NT, bool GX>
+template <int NT, bool GX, int SB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                      const __grid_constant__ CUtensorMap tmLN, int M, int N, int K, GemmEpilogue ep) {
-  using Cfg = RowLnCfg<NT>;
+  using Cfg = RowLnCfg<NT, SB>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BLOCK_N = 256;
 
@@ -761,9 +812,9 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };           // per CTA (multicast commit)
   auto tfull_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + s); };       // per CTA (multicast commit)
   auto tempty_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + 2 + s); };  // used in the pair leader only
-  const uint32_t rbar_base = bar_base + 8u * (2 * STAGES + 4);                         // 8 warps x 2 residual-load barriers
-  auto stat_bar = [&](uint32_t s) { return rbar_base + 8u * 16 + 8u * s; };            // per tile parity: partials have landed
-  const uint32_t tmem_slot = rbar_base + 8u * 16 + 8u * 2;
+  const uint32_t rbar_base = bar_base + 8u * (2 * STAGES + 4);                         // 8 warps x 4 residual-load barriers
+  auto stat_bar = [&](uint32_t s) { return rbar_base + 8u * 32 + 8u * s; };            // per tile parity: partials have landed
+  const uint32_t tmem_slot = rbar_base + 8u * 32 + 8u * 2;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5;
@@ -793,9 +844,9 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 16);          // one arrive per epilogue warp of both CTAs of the pair
-      mbar_init(stat_bar(s), NT * 8 * 32);   // one arrive per epilogue LANE of every CTA that holds these rows
+      mbar_init(stat_bar(s), NT * 8);        // one arrive per epilogue WARP of every CTA that holds these rows
     }
-    for (int s = 0; s < 16; ++s) mbar_init(rbar_base + 8u * s, 1);
+    for (int s = 0; s < 32; ++s) mbar_init(rbar_base + 8u * s, 1);
     mbar_fence_init();
   }
   cluster_sync_all();  // barriers of all CTAs initialised before anyone signals across the cluster
@@ -816,6 +867,8 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int rbe = ep.reverse ? row_blocks - 1 - rb : rb;
       const int m0 = rbe * 2 * BLOCK_M + static_cast<int>(half) * BLOCK_M;       // this CTA's 128 rows
       const int n0 = static_cast<int>(pair) * BLOCK_N + static_cast<int>(half) * (BLOCK_N / 2);   // its half of the weight rows
+      const int rbn = rb + n_clusters;
+      const int m0_next = rbn < row_blocks ? (ep.reverse ? row_blocks - 1 - rbn : rbn) * 2 * BLOCK_M + static_cast<int>(half) * BLOCK_M : -1;
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         if (elect_one()) {
@@ -824,6 +877,8 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
           tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * BLOCK_K, n0);
           if (!leader) mbar_arrive_remote(full_bar(stage), leader_rank);
+          // (the NT pairs of a row block read the same A rows: only the first pair prefetches them)
+          if (pair == 0) prefetch_a_ahead(&tmA, ep.a_prefetch, kb, k_blocks, m0, m0_next);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -836,7 +891,9 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       uint32_t stage = 0, phase = 0, iter = 0;
       for (int rb = cluster_id; rb < row_blocks; rb += n_clusters, ++iter) {
         const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
+        RTRACE(2, iter, 0);
         mbar_wait(tempty_bar(as), aphase ^ 1u);
+        RTRACE(2, iter, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -855,25 +912,30 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        RTRACE(2, iter, 2);
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (every CTA, its 128 rows x the pair's 256 columns) =====================
-    constexpr int HALF_N = BLOCK_N / 2, CHUNKS = HALF_N / 32;
-    const int ew = warp & 3, chalf = (warp - 4) >> 2;
-    EpiCtx cx{0u, stg_base + (warp - 4) * 2 * BOX_BYTES, rbar_base + 16u * (warp - 4), 0u, 0u};
+    constexpr int CW = BLOCK_N / 2, CHUNKS = CW / 32;
+    constexpr float CWF = static_cast<float>(CW);
+    const int ew = warp & 3, cslice = (warp - 4) >> 2;     // TMEM lane quarter, column half of this warp
+    EpiCtx cx{0u, stg_base + (warp - 4) * SB * BOX_BYTES, rbar_base + 32u * (warp - 4), 0u, 0u};
     const uint32_t my_row = static_cast<uint32_t>(ew * 32 + lane);                 // row inside this CTA's 128
-    const uint32_t my_slot = pair * 2u + static_cast<uint32_t>(chalf);
+    const uint32_t my_slot = pair * 2u + static_cast<uint32_t>(cslice);
     const float inv_n = 1.0f / static_cast<float>(NT * BLOCK_N);
     uint32_t iter = 0;
     for (int rb = cluster_id; rb < row_blocks; rb += n_clusters, ++iter) {
       const int rbe = ep.reverse ? row_blocks - 1 - rb : rb;
       const int row0 = rbe * 2 * BLOCK_M + static_cast<int>(half) * BLOCK_M + ew * 32;
-      const int col0 = static_cast<int>(pair) * BLOCK_N + chalf * HALF_N;
+      const int col0 = static_cast<int>(pair) * BLOCK_N + cslice * CW;
       const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
-      const uint32_t taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16) + chalf * HALF_N;
+      const uint32_t taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16) + cslice * CW;
       const bool rows_live = row0 < M;     // (a warp entirely below the matrix still takes part in the exchange)
-      if (rows_live) resid_issue_load<2>(&tmR, N, row0, col0, cx, lane);
+      // all SB boxes are free here (the previous tile ended with a read-out wait): the first SB residual chunks of this
+      // tile are requested before its accumulator is ready
+      if (rows_live)
+        for (int c = 0; c < SB; ++c) rowln_issue_resid<SB>(&tmR, row0, col0 + 32 * c, cx, lane);
       {   // residual boxes of this CTA's next row block: into L2 a whole main loop ahead
         const int nrb = rb + n_clusters;
         if (nrb < row_blocks && lane == 0) {
@@ -883,8 +945,11 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int c = 0; c < CHUNKS; ++c) tma_prefetch_l2_2d(&tmR, col0 + 32 * c, nr);
         }
       }
+      const int tslot = warp == 4 ? 0 : warp == 11 ? 1 : -1;   // (trace builds only)
+      if (tslot >= 0) RTRACE(tslot, iter, 0);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      if (tslot >= 0) RTRACE(tslot, iter, 1);
       // ---------------- pass 1: x' = acc + bias + x -> fp32 out, back into TMEM, running (mean, M2) of this row
       float run_mean = 0.f, run_m2 = 0.f;
       if (rows_live) {
@@ -893,30 +958,39 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int n0 = col0 + 32 * c;
           uint32_t v[32];
           tmem_ld32(taddr + 32 * c, v);
-          if (c + 1 < CHUNKS) resid_issue_load<2>(&tmR, N, row0, n0 + 32, cx, lane);
+          // (loads are batched — bias, then the eight 16-byte units of this lane's residual row, then the arithmetic, then
+          // the eight stores: interleaved, every unit sat out its own shared-memory / L1 round trip, ~1500 cycles per chunk)
+          float4 bq[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bq[j] = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
           tmem_ld_wait();
-          const uint32_t buf = cx.stg + (cx.n_use % 2) * BOX_BYTES;
-          mbar_wait(cx.rbar + 8u * (cx.n_use & 1u), (cx.n_use >> 1) & 1u);  // residual box has landed
+          const uint32_t box = cx.n_use % SB;
+          const uint32_t buf = cx.stg + box * BOX_BYTES;
+          mbar_wait(cx.rbar + 8u * box, (cx.n_use / SB) & 1u);  // residual box has landed
           ++cx.n_use;
+          float4 r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = buf + lane * 128 + ((j ^ (lane & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r[j].x), "=f"(r[j].y), "=f"(r[j].z), "=f"(r[j].w) : "r"(a));
+          }
           float csum = 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int n = n0 + 4 * j;
+            r[j].x += __uint_as_float(v[4 * j + 0]) + bq[j].x;
+            r[j].y += __uint_as_float(v[4 * j + 1]) + bq[j].y;
+            r[j].z += __uint_as_float(v[4 * j + 2]) + bq[j].z;
+            r[j].w += __uint_as_float(v[4 * j + 3]) + bq[j].w;
+            v[4 * j + 0] = __float_as_uint(r[j].x);
+            v[4 * j + 1] = __float_as_uint(r[j].y);
+            v[4 * j + 2] = __float_as_uint(r[j].z);
+            v[4 * j + 3] = __float_as_uint(r[j].w);
+            csum += (r[j].x + r[j].y) + (r[j].z + r[j].w);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
             const uint32_t a = buf + lane * 128 + ((j ^ (lane & 7)) << 4);
-            float4 r;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory");
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ep.bias) b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-            r.x += __uint_as_float(v[4 * j + 0]) + b.x;
-            r.y += __uint_as_float(v[4 * j + 1]) + b.y;
-            r.z += __uint_as_float(v[4 * j + 2]) + b.z;
-            r.w += __uint_as_float(v[4 * j + 3]) + b.w;
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r.x), "f"(r.y), "f"(r.z), "f"(r.w) : "memory");
-            v[4 * j + 0] = __float_as_uint(r.x);
-            v[4 * j + 1] = __float_as_uint(r.y);
-            v[4 * j + 2] = __float_as_uint(r.z);
-            v[4 * j + 3] = __float_as_uint(r.w);
-            csum += (r.x + r.y) + (r.z + r.w);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r[j].x), "f"(r[j].y), "f"(r[j].z), "f"(r[j].w) : "memory");
           }
           tmem_st32(taddr + 32 * c, v);   // x' back into the accumulator columns it came from (read again in pass 2)
           fence_proxy_async_smem();
@@ -924,6 +998,12 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (lane == 0) {
             tma_store_2d(&tmC, buf, n0, row0);
             tma_store_commit();
+          }
+          // chunk c + SB - 1 goes into the box chunk c - 1 was stored from: that store (all but the latest) must have
+          // read it out
+          if (c >= 1 && c + SB - 1 < CHUNKS) {
+            if (lane == 0) tma_store_wait_read<1>();
+            rowln_issue_resid<SB>(&tmR, row0, n0 + 32 * (SB - 1), cx, lane);
           }
           // Welford over the chunk, Chan's combination with the running statistics of the chunks before it
           const float cmean = csum * (1.0f / 32.0f);
@@ -937,15 +1017,17 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const float delta = cmean - run_mean;
           run_mean += delta * (32.0f / ntot);
           run_m2 += cm2 + delta * delta * (na * 32.0f / ntot);
+          if (tslot >= 0) RTRACE(tslot, iter, 2 + c);
         }
         tmem_st_wait();
       }
-      // ---------------- exchange: this row's partial to every CTA of the cluster that holds the same rows
+      if (tslot >= 0) RTRACE(tslot, iter, 6);
+      // ---------------- exchange: this row's partial to every CTA that holds the same rows
       const long long m_pad = static_cast<long long>(row_blocks) * 2 * BLOCK_M;
       const float2* gpart = reinterpret_cast<const float2*>(ep.ln_scratch) + (row0 + lane);   // + slot * m_pad
       if (GX) {
         // global exchange: partial -> scratch[slot][row] (coalesced), one release-arrive per warp on the counter of
-        // (row block, M half, lane quarter), then wait until all 2 NT warps that hold these rows have arrived.  Warps
+        // (row block, M half, lane quarter), then wait until all STAT_SLOTS warps that hold these rows have arrived.  Warps
         // entirely below the matrix have no partners and skip both.
         if (rows_live) {
           float2* part = reinterpret_cast<float2*>(ep.ln_scratch);
@@ -967,74 +1049,87 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           __syncwarp();
         }
       } else {
+        // every lane stores its row's partial into the NT CTAs that hold the same rows; then ONE cluster-scope fence and
+        // NT arrives per WARP (a release-arrive per lane and target made every lane sit out three store round trips:
+        // 14-19 % of the epilogue warps' samples were membar stalls, profiles/r02_layer_ncu_v1.md)
         const uint32_t slot_addr = stat_base + ((as * Cfg::STAT_SLOTS + my_slot) * 128u + my_row) * 8u;
 #pragma unroll
-        for (uint32_t p = 0; p < static_cast<uint32_t>(NT); ++p) {
-          const uint32_t target = 2u * p + half;
-          st_cluster_f2(mapa_u32(slot_addr, target), run_mean, run_m2);
-          mbar_arrive_cluster_release(mapa_u32(stat_bar(as), target));
+        for (uint32_t p = 0; p < static_cast<uint32_t>(NT); ++p) st_cluster_f2(mapa_u32(slot_addr, 2u * p + half), run_mean, run_m2);
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("fence.acq_rel.cluster;" ::: "memory");
+#pragma unroll
+          for (uint32_t p = 0; p < static_cast<uint32_t>(NT); ++p) mbar_arrive_cluster_release(mapa_u32(stat_bar(as), 2u * p + half));
         }
+        if (tslot >= 0) RTRACE(tslot, iter, 7);
         mbar_wait_cluster_acquire(stat_bar(as), aphase);
       }
+      if (tslot >= 0) RTRACE(tslot, iter, 8);
       // ---------------- pass 2: LayerNorm of x' from TMEM -> 16-bit rows
       if (rows_live) {
         float mean = 0.f, m2 = 0.f;
         const float2* sp = reinterpret_cast<const float2*>(smem_gen + (stat_base - smem_base)) + (as * Cfg::STAT_SLOTS) * 128u + my_row;
 #pragma unroll
-        for (uint32_t s = 0; s < Cfg::STAT_SLOTS; ++s) {   // Chan: partials of 128 values each
+        for (uint32_t s = 0; s < Cfg::STAT_SLOTS; ++s) {   // Chan: partials of CW values each
           const float2 pm = GX ? __ldcg(gpart + s * m_pad) : sp[s * 128u];
-          const float na = 128.0f * static_cast<float>(s), ntot = na + 128.0f;
+          const float na = CWF * static_cast<float>(s), ntot = na + CWF;
           const float delta = pm.x - mean;
-          mean += delta * (128.0f / ntot);
-          m2 += pm.y + delta * delta * (na * 128.0f / ntot);
+          mean += delta * (CWF / ntot);
+          m2 += pm.y + delta * delta * (na * CWF / ntot);
         }
         const float rstd = rsqrtf(m2 * inv_n + 1e-5f);
         tc_fence_after();
 #pragma unroll 1
-        for (int c2 = 0; c2 < CHUNKS / 2; ++c2) {       // 64 columns = one 128-byte row of the 16-bit box
-          const int n0 = col0 + 64 * c2;
-          uint32_t v[64];
-          tmem_ld32(taddr + 64 * c2, v);
-          tmem_ld32(taddr + 64 * c2 + 32, v + 32);
-          tmem_ld_wait();
-          if (c2 == CHUNKS / 2 - 1) {   // everything of this tile is in registers: hand the accumulator stage back to the leader
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(tempty_bar(as), leader_rank);
-          }
-          const uint32_t buf = cx.stg + (c2 & 1) * BOX_BYTES;
+        for (int c2 = 0; c2 < CW / 64; ++c2) {          // 64 columns = one 128-byte row of the 16-bit box
+          const uint32_t buf = cx.stg + c2 * BOX_BYTES;
           if (lane == 0) tma_store_wait_read<0>();     // every earlier store of this warp has read its box
           __syncwarp();
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {                 // 32 columns at a time (register budget at 16 epilogue warps)
+            const int n0 = col0 + 64 * c2 + 32 * h;
+            uint32_t v[32];
+            tmem_ld32(taddr + 64 * c2 + 32 * h, v);
+            float4 gq[8], bq[8];      // gamma / beta of these 32 columns: in flight together with the TMEM read
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int n = n0 + 8 * j;
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + n));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + n + 4));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + n));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + n + 4));
-            float y[8];
-            y[0] = fmaf((__uint_as_float(v[8 * j + 0]) - mean) * rstd, g0.x, b0.x);
-            y[1] = fmaf((__uint_as_float(v[8 * j + 1]) - mean) * rstd, g0.y, b0.y);
-            y[2] = fmaf((__uint_as_float(v[8 * j + 2]) - mean) * rstd, g0.z, b0.z);
-            y[3] = fmaf((__uint_as_float(v[8 * j + 3]) - mean) * rstd, g0.w, b0.w);
-            y[4] = fmaf((__uint_as_float(v[8 * j + 4]) - mean) * rstd, g1.x, b1.x);
-            y[5] = fmaf((__uint_as_float(v[8 * j + 5]) - mean) * rstd, g1.y, b1.y);
-            y[6] = fmaf((__uint_as_float(v[8 * j + 6]) - mean) * rstd, g1.z, b1.z);
-            y[7] = fmaf((__uint_as_float(v[8 * j + 7]) - mean) * rstd, g1.w, b1.w);
-            const uint32_t p0 = pack16x2(y[0], y[1], ep.fp16), p1 = pack16x2(y[2], y[3], ep.fp16);
-            const uint32_t p2 = pack16x2(y[4], y[5], ep.fp16), p3 = pack16x2(y[6], y[7], ep.fp16);
-            const uint32_t dst = buf + lane * 128 + ((j ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+            for (int j = 0; j < 8; ++j) {
+              gq[j] = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + n0 + 4 * j));
+              bq[j] = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + n0 + 4 * j));
+            }
+            tmem_ld_wait();
+            if (c2 == CW / 64 - 1 && h == 1) {   // everything of this tile is in registers: hand the accumulator stage back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_remote(tempty_bar(as), leader_rank);
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float y0 = fmaf((__uint_as_float(v[4 * j + 0]) - mean) * rstd, gq[j].x, bq[j].x);
+              const float y1 = fmaf((__uint_as_float(v[4 * j + 1]) - mean) * rstd, gq[j].y, bq[j].y);
+              const float y2 = fmaf((__uint_as_float(v[4 * j + 2]) - mean) * rstd, gq[j].z, bq[j].z);
+              const float y3 = fmaf((__uint_as_float(v[4 * j + 3]) - mean) * rstd, gq[j].w, bq[j].w);
+              pk[2 * j] = pack16x2(y0, y1, ep.fp16);
+              pk[2 * j + 1] = pack16x2(y2, y3, ep.fp16);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t unit = static_cast<uint32_t>(4 * h + j);     // 16-B unit inside the 128-B box row
+              const uint32_t dst = buf + lane * 128 + ((unit ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]),
+                           "r"(pk[4 * j + 3]) : "memory");
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmLN, buf, n0, row0);
+            tma_store_2d(&tmLN, buf, col0 + 64 * c2, row0);
             tma_store_commit();
           }
+          if (tslot >= 0) RTRACE(tslot, iter, 9 + c2);
         }
         if (lane == 0) tma_store_wait_read<0>();   // the boxes are refilled by the next tile's residual loads
         __syncwarp();
+        if (tslot >= 0) RTRACE(tslot, iter, 11);
       } else {
         tc_fence_before();
         __syncwarp();
@@ -1126,17 +1221,17 @@ int launch_pair(const void* A, long long lda, const void* B, long long ldb, int 
   return 0;
 }
 
-template <int NT, bool GX>
+template <int NT, bool GX, int SB>
 int launch_rowln(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                  const GemmEpilogue& ep, cudaStream_t stream) {
-  using Cfg = RowLnCfg<NT>;
+  using Cfg = RowLnCfg<NT, SB>;
   constexpr int CLUSTER = GX ? 2 : 2 * NT;   // hardware cluster: the CTA pair (global exchange) or the whole row block
   Maps mp;
   int rc = build_maps(mp, A, lda, B, ldb, M, N, K, ep, EPI_F32_RESID, 128);
   if (rc) return rc;
   rc = make_tmap_2d(&mp.c16, ep.ln_out, 2, M, N, ep.ld_ln, 32, 64);
   if (rc) return rc;
-  auto kern = gemm_tn_rowln_kernel<NT, GX>;
+  auto kern = gemm_tn_rowln_kernel<NT, GX, SB>;
   static PerDeviceOnce attr;
   static PerDeviceSize max_groups;   // co-resident row-block groups of 2 NT CTAs (one CTA per SM) on this device
   if (attr.first()) {
@@ -1203,8 +1298,20 @@ size_t gemm_ln_scratch_bytes(long long M, int N) {
 }
 
 int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
-            const GemmEpilogue& ep, cudaStream_t stream, int force_block_n) {
+            const GemmEpilogue& ep_in, cudaStream_t stream, int force_block_n) {
   OVMR_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  GemmEpilogue ep = ep_in;
+  if (ep.a_prefetch < 0) {
+    // default policy: OVMR_A_PREFETCH=<distance>[:<min K>] overrides (A/B measurements)
+    static const int env_dist = [] { const char* e = getenv("OVMR_A_PREFETCH"); return e ? atoi(e) : -1; }();
+    static const int env_mink = [] {
+      const char* e = getenv("OVMR_A_PREFETCH");
+      const char* c = e ? strchr(e, ':') : nullptr;
+      return c ? atoi(c + 1) : 0;
+    }();
+    if (env_dist >= 0) ep.a_prefetch = K >= env_mink ? env_dist : 0;
+    else ep.a_prefetch = 0;
+  }
   OVMR_REQUIRE(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0,
                "gemm: K, N, lda, ldb must be multiples of 8 (K=%d N=%d lda=%lld ldb=%lld)", K, N, lda, ldb);
   OVMR_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
@@ -1257,16 +1364,18 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, i
                      (reinterpret_cast<uintptr_t>(ep.ln_out) & 15) == 0 && (N == 512 || N == 768 || N == 1024),
                  "gemm: the LayerNorm-emitting residual epilogue needs the TMA residual path, gamma / beta, an aligned "
                  "16-bit output and N in {512, 768, 1024} (N=%d)", N);
+    // (RowLnCfg<NT, 3> — three staging boxes, three ring stages — measured no faster at K = 768 and slower at K = 3072:
+    // profiles/r02_rowln_trace.md; only the two-box form is instantiated)
     if (ep.ln_scratch != nullptr) {
       OVMR_REQUIRE((reinterpret_cast<uintptr_t>(ep.ln_scratch) & 15) == 0 && ep.ln_gen > 0 && ep.ln_gen < (1u << 24),
                    "gemm: the global LayerNorm exchange needs an aligned scratch and a generation in [1, 2^24)");
-      if (N == 512) return launch_rowln<2, true>(A, lda, B, ldb, M, N, K, ep, stream);
-      if (N == 768) return launch_rowln<3, true>(A, lda, B, ldb, M, N, K, ep, stream);
-      return launch_rowln<4, true>(A, lda, B, ldb, M, N, K, ep, stream);
+      if (N == 512) return launch_rowln<2, true, 2>(A, lda, B, ldb, M, N, K, ep, stream);
+      if (N == 768) return launch_rowln<3, true, 2>(A, lda, B, ldb, M, N, K, ep, stream);
+      return launch_rowln<4, true, 2>(A, lda, B, ldb, M, N, K, ep, stream);
     }
-    if (N == 512) return launch_rowln<2, false>(A, lda, B, ldb, M, N, K, ep, stream);
-    if (N == 768) return launch_rowln<3, false>(A, lda, B, ldb, M, N, K, ep, stream);
-    return launch_rowln<4, false>(A, lda, B, ldb, M, N, K, ep, stream);
+    if (N == 512) return launch_rowln<2, false, 2>(A, lda, B, ldb, M, N, K, ep, stream);
+    if (N == 768) return launch_rowln<3, false, 2>(A, lda, B, ldb, M, N, K, ep, stream);
+    return launch_rowln<4, false, 2>(A, lda, B, ldb, M, N, K, ep, stream);
   }
   if (tma_resid) return dispatch_tile<EPI_F32_RESID>(bn, A, lda, B, ldb, M, N, K, ep, stream);
   return dispatch_tile<EPI_GENERIC>(bn, A, lda, B, ldb, M, N, K, ep, stream);

@@ -55,6 +55,8 @@ struct GemmEpilogue {
   // 18 instead of 16 at N = 1024 on a B200).  nullptr: the cluster / DSMEM form.
   void* ln_scratch = nullptr;
   unsigned ln_gen = 0;
+  int a_prefetch = -1;  // L2 prefetch distance of the A operand in 64-column K blocks (CTA-pair kernels); -1 = default
+                        // (OVMR_A_PREFETCH, else 8 when A is streamed from HBM — K >= 2048 — and 0 otherwise), 0 = off
   int reverse = 0;  // walk the output tiles last-to-first (see api.cu: alternating sweep direction keeps the
                     // rows the previous kernel wrote last — still resident in L2 — first in line)
 };
