@@ -171,6 +171,17 @@ int ovmr_attention(const void* qkv, void* out, int n_seq, int seq_len, int width
 int ovmr_attention_impl(const void* qkv, void* out, int n_seq, int seq_len, int width, int heads, int causal,
                         int fp16, int impl, void* stream);
 
+/* VisionTransformer.conv1 + positional embedding as an IMPLICIT GEMM (clip/model.py:366, 412-416): no patch matrix is
+ * written; the kernel's producer warps read each patch from the NCHW images — fp32 (is_u8 = 0) or uint8 with the reference's
+ * ToTensor + Normalize applied on the fly (is_u8 = 1, mean_std = HOST pointer to mean RGB, std RGB; rejected if the
+ * division-free normalisation is not bit-identical to the IEEE one for that mean / std) — and the epilogue adds
+ * positional_embedding[1 + t] and writes patch t of image b to row b * (G*G + 1) + 1 + t of x fp32 [batch * (G*G + 1), width]
+ * (CLS rows untouched).  conv_w: conv1.weight.reshape(D, -1), 16-bit [width, k_pad], zero padded.  This is what the vision
+ * tower runs; ovmr_patchify(_u8) + ovmr_gemm_tn remain as the explicit form (OVMR_IMPLICIT_PATCH=0). */
+int ovmr_patch_embed(const void* images, int is_u8, const float* mean_std, int batch, int resolution, int patch,
+                     const void* conv_w, int k_pad, const float* positional_embedding, float* x, int width, int fp16,
+                     void* stream);
+
 /* conv1 input as GEMM operand (clip/model.py:412-414): fp32 NCHW -> bf16 [batch*G*G, ldo]. */
 int ovmr_patchify(const float* images, void* out_16bit, int batch, int resolution, int patch, int ldo, int fp16,
                   void* stream);

@@ -66,6 +66,8 @@ SIGNATURES = {
                                c_void_p, c_ll, c_void_p, c_void_p, c_int, c_void_p]),
     "ovmr_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ovmr_attention_impl": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ovmr_patch_embed": (c_int, [c_void_p, c_int, C.POINTER(c_float), c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                 c_int, c_int, c_void_p]),
     "ovmr_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ovmr_patchify_u8": (c_int, [c_void_p, C.POINTER(c_float), c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ovmr_resample_coeffs": (c_int, [c_int, c_int, c_int, C.POINTER(c_int), C.POINTER(c_int), c_int]),

@@ -3,6 +3,7 @@
 #include "../../include/ovmr_b200.h"
 
 #include <cstdlib>
+#include <cstring>
 
 #include "attention.cuh"
 #include "common.cuh"
@@ -97,6 +98,27 @@ static bool ln_global_exchange() {
     return e != nullptr && e[0] == 'g';
   }();
   return on;
+}
+
+// Patch embedding as an implicit GEMM (gemm.cuh: patch_embed) when OVMR_IMPLICIT_PATCH=1 — built, bit-identical to the explicit
+// form, but measured SLOWER on B200 (512 ViT-B/16 images: 436 us against 194 + 195 us; profiles/r02_patch_embed.md), so the
+// towers keep patchify + GEMM by default — unless the patch size is not a multiple of 8
+// (ViT-L/14), the image pointer is not aligned for vector loads, or — uint8 input — the producer's division-free normalisation is not bit-identical to the reference's
+// ToTensor + Normalize for this mean / std (checked once per distinct mean / std); then patchify + GEMM as before.
+static bool implicit_patch_embed(const float* mean_std, const void* images, bool u8, int R, int P) {
+  static const bool enabled = [] {
+    const char* e = getenv("OVMR_IMPLICIT_PATCH");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (!enabled || P % 8 != 0 || R % 8 != 0 || (reinterpret_cast<uintptr_t>(images) & (u8 ? 7 : 31)) != 0) return false;
+  if (mean_std == nullptr) return true;
+  static thread_local float checked[6] = {0, 0, 0, 0, 0, 0};
+  static thread_local int verdict = -1;
+  if (verdict < 0 || memcmp(checked, mean_std, sizeof(checked)) != 0) {
+    memcpy(checked, mean_std, sizeof(checked));
+    verdict = ovmr::patch_embed_u8_exact(mean_std) ? 1 : 0;
+  }
+  return verdict == 1;
 }
 
 #define RET_IF(expr)        \
@@ -310,17 +332,26 @@ static int vit_forward_impl(const ovmr_vit* v, const float* images, const uint8_
   // conv1 as a GEMM over patchified pixels; epilogue adds positional_embedding[1+t] and scatters
   // patch t of image b to row b*L + 1 + t; CLS rows = class_embedding + positional_embedding[0].
   const int fp16 = v->transformer.fp16 != 0;
-  if (images_u8)
-    RET_IF(ovmr::patchify_u8(images_u8, mean_std, patches, batch, v->resolution, v->patch, v->k_pad, fp16, st));
-  else
-    RET_IF(ovmr::patchify(images, patches, batch, v->resolution, v->patch, v->k_pad, fp16, st));
-  RET_IF(ovmr::cls_rows(x, v->class_embedding, v->positional_embedding, batch, L, D, st));
-  GemmEpilogue pe;
-  pe.resid = v->positional_embedding; pe.ldr = D; pe.out = x; pe.ldo = D; pe.out_bf16 = 0; pe.row_grp = G * G; pe.fp16 = fp16;
   Sweep sw;
-  sw.next();  // patchify walked the images first-to-last
-  pe.reverse = sw.next();
-  RET_IF(ovmr::gemm_tn(patches, v->k_pad, v->conv_w, v->k_pad, batch * G * G, D, v->k_pad, pe, st));
+  if (implicit_patch_embed(images_u8 ? mean_std : nullptr, images ? static_cast<const void*>(images) : images_u8, images_u8 != nullptr,
+                           v->resolution, v->patch)) {
+    // implicit GEMM: the kernel's producer warps read the patches from the NCHW images (no patch matrix in HBM)
+    RET_IF(ovmr::cls_rows(x, v->class_embedding, v->positional_embedding, batch, L, D, st));
+    RET_IF(ovmr::patch_embed(images ? static_cast<const void*>(images) : images_u8, images_u8 != nullptr, mean_std, batch, v->resolution,
+                             v->patch, v->conv_w, v->k_pad, v->positional_embedding, x, D, fp16, st));
+    sw.next();   // walked the rows first-to-last
+  } else {
+    if (images_u8)
+      RET_IF(ovmr::patchify_u8(images_u8, mean_std, patches, batch, v->resolution, v->patch, v->k_pad, fp16, st));
+    else
+      RET_IF(ovmr::patchify(images, patches, batch, v->resolution, v->patch, v->k_pad, fp16, st));
+    RET_IF(ovmr::cls_rows(x, v->class_embedding, v->positional_embedding, batch, L, D, st));
+    GemmEpilogue pe;
+    pe.resid = v->positional_embedding; pe.ldr = D; pe.out = x; pe.ldo = D; pe.out_bf16 = 0; pe.row_grp = G * G; pe.fp16 = fp16;
+    sw.next();  // patchify walked the images first-to-last
+    pe.reverse = sw.next();
+    RET_IF(ovmr::gemm_tn(patches, v->k_pad, v->conv_w, v->k_pad, batch * G * G, D, v->k_pad, pe, st));
+  }
   // ln_pre (fp32, in place) chained with layer 0's ln_1 (bf16 operand of the first QKV GEMM)
   const ovmr_block_weights& b0 = v->transformer.blocks[0];
   if (tower_folded(&v->transformer))   // ln_pre in place + 16-bit copy / row statistics for layer 0's folded ln_1
@@ -416,6 +447,15 @@ int ovmr_attention_impl(const void* qkv, void* out, int n_seq, int seq_len, int 
                         int impl, void* stream) {
   OVMR_REQUIRE(impl >= 0 && impl <= 3, "attention_impl: impl=%d", impl);
   return ovmr::attention(qkv, out, n_seq, seq_len, width, heads, causal, fp16 != 0, S(stream), 0, impl);
+}
+
+int ovmr_patch_embed(const void* images, int is_u8, const float* mean_std, int batch, int resolution, int patch,
+                     const void* conv_w, int k_pad, const float* positional_embedding, float* x, int width, int fp16, void* stream) {
+  OVMR_REQUIRE(!is_u8 || mean_std != nullptr, "patch_embed: uint8 input needs mean / std");
+  OVMR_REQUIRE(!is_u8 || ovmr::patch_embed_u8_exact(mean_std),
+               "patch_embed: the division-free normalisation is not exact for this mean / std (use ovmr_patchify_u8 + ovmr_gemm_tn)");
+  return ovmr::patch_embed(images, is_u8 != 0, mean_std, batch, resolution, patch, conv_w, k_pad, positional_embedding, x, width,
+                           fp16 != 0, S(stream));
 }
 
 int ovmr_patchify(const float* images, void* out_16bit, int batch, int resolution, int patch, int ldo, int fp16,

@@ -28,12 +28,19 @@
 //   EPI_F32_RESID  fp32 out = acc + bias + resid: the residual box (32 rows x 32 cols) is TMA-LOADED into the
 //                  staging buffer one chunk ahead (and L2-prefetched one tile ahead), updated in place by the
 //                  owning threads and TMA-stored.
+//   EPI_F32_SCATTER  the patch-embed epilogue (row_grp > 0): fp32 out = acc + positional_embedding[1 + m % G], token m of
+//                  image m / G written to row (m / G)(G + 1) + 1 + m % G.  A warp's 32 tokens are 32 consecutive output
+//                  rows unless they straddle two images: swizzled box + one 2-D TMA store in the common case, direct
+//                  128-byte-per-lane stores for a straddling warp.  (The transposing direct-store form of EPI_GENERIC ran
+//                  this epilogue at 195 us per 512 ViT-B/16 images against 123 us without scatter and positional rows.)
 //   EPI_F32_RESID_EMIT / EPI_16(_GELU)_LN   the two halves of LayerNorm folding (gemm.cuh): the residual epilogue
 //                  also stores a 16-bit copy of its rows plus per-row slab statistics, the 16-bit epilogue applies
 //                  rstd * (acc - mean * colsum) + bias'.  Parity-tested, off by default (measured slower in situ).
 // All launches carry the programmatic-dependent-launch attribute: the prologue above pdl_wait() overlaps the tail
 // of the previous kernel.  `ep.reverse` walks the tiles last-to-first (alternating sweep direction, api.cu).
 #include "gemm.cuh"
+
+#include <type_traits>
 
 #include <stdlib.h>
 #include <string.h>
@@ -51,7 +58,8 @@ constexpr int GEMM_THREADS = 384;         // 4 control warps + 8 epilogue warps
 constexpr uint32_t BOX_BYTES = 32 * 128;  // one epilogue staging box: 32 rows x 128 B
 
 enum EpiMode { EPI_GENERIC = 0, EPI_16 = 1, EPI_16_GELU = 2, EPI_F32_RESID = 3, EPI_F32_RESID_EMIT = 4,
-               EPI_16_LN = 5, EPI_16_GELU_LN = 6 };  // _LN: folded LayerNorm applied in the 16-bit epilogue
+               EPI_16_LN = 5, EPI_16_GELU_LN = 6,   // _LN: folded LayerNorm applied in the 16-bit epilogue
+               EPI_F32_SCATTER = 7 };               // patch-embed: + positional row, TMA store behind the CLS rows
 
 __device__ __forceinline__ float quick_gelu(float x) {
   // x * sigmoid(1.702 x) with sigmoid(y) = 0.5 + 0.5 tanh(y/2): one MUFU op per element
@@ -242,6 +250,69 @@ __device__ __forceinline__ void epilogue_f32_resid(const GemmEpilogue& ep, const
 }
 
 // ---------------------------------------------------------------------------------------------
+// EPI_F32_SCATTER: fp32 out = acc + pos[1 + m % G], 32 columns at a time.  A warp's 32 token rows land on 32 CONSECUTIVE
+// output rows (shifted by the CLS rows before them) unless they straddle two images: the common case goes through the
+// swizzled staging box and one 2-D TMA store; a straddling warp (32 of every G rows) writes its rows directly, 128 bytes
+// per lane.
+// ---------------------------------------------------------------------------------------------
+template <int HALF_N, int STG_BUFS, bool PAIR>
+__device__ __forceinline__ void epilogue_scatter(const GemmEpilogue& ep, const CUtensorMap* tmC, int M, int N, int row0, int col0,
+                                                 uint32_t taddr, uint32_t tempty, EpiCtx& cx, int lane) {
+  constexpr int CHUNKS = HALF_N / 32;
+  const int G2 = ep.row_grp;
+  const int b0 = row0 / G2, t0 = row0 - b0 * G2;        // image and patch of this warp's first row
+  const int m = row0 + lane;
+  const bool wrapped = t0 + lane >= G2;                 // (32 <= G: at most one image boundary inside the warp)
+  const int t = t0 + lane - (wrapped ? G2 : 0);
+  const float* prow = ep.resid + static_cast<long long>(1 + t) * ep.ldr;
+  const bool straddles = t0 + 32 > G2;
+  const int orow0 = row0 + b0 + 1;                      // output row of this warp's first token
+  float* orow = reinterpret_cast<float*>(ep.out) + static_cast<long long>(m + b0 + 1 + (wrapped ? 1 : 0)) * ep.ldo;
+#pragma unroll 1
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int n0 = col0 + 32 * c;
+    uint32_t v[32];
+    tmem_ld32(taddr + 32 * c, v);
+    float4 pq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      pq[j] = (m < M && n0 + 4 * j + 4 <= N) ? __ldg(reinterpret_cast<const float4*>(prow + n0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    tmem_ld_wait();
+    if (c == CHUNKS - 1) release_accumulator<PAIR>(tempty, lane);
+    if (n0 >= N) continue;
+    if (straddles) {
+      if (m < M) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n0 + 4 * j + 4 <= N)
+            *reinterpret_cast<float4*>(orow + n0 + 4 * j) =
+                make_float4(__uint_as_float(v[4 * j + 0]) + pq[j].x, __uint_as_float(v[4 * j + 1]) + pq[j].y,
+                            __uint_as_float(v[4 * j + 2]) + pq[j].z, __uint_as_float(v[4 * j + 3]) + pq[j].w);
+      }
+      continue;
+    }
+    const uint32_t buf = cx.stg + (cx.n_use % STG_BUFS) * BOX_BYTES;
+    ++cx.n_use;
+    if (lane == 0) tma_store_wait_read<STG_BUFS - 1>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t dst = buf + lane * 128 + ((j ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(__uint_as_float(v[4 * j + 0]) + pq[j].x),
+                   "f"(__uint_as_float(v[4 * j + 1]) + pq[j].y), "f"(__uint_as_float(v[4 * j + 2]) + pq[j].z),
+                   "f"(__uint_as_float(v[4 * j + 3]) + pq[j].w)
+                   : "memory");
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmC, buf, n0, orow0);   // rows past the last image / columns past N are clipped by the tensor map
+      tma_store_commit();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // EPI_GENERIC: tcgen05.ld -> per-warp smem transpose -> alpha/bias/act/residual/row scatter -> coalesced stores.
 // ---------------------------------------------------------------------------------------------
 template <int HALF_N, bool PAIR>
@@ -365,6 +436,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, const CUte
     epilogue_f32_resid<HALF_N, STG_BUFS, PAIR, false>(ep, tmC, tmR, tmC16, M, N, row0, col0, taddr, tempty, cx, lane);
   else if (MODE == EPI_F32_RESID_EMIT)
     epilogue_f32_resid<HALF_N, STG_BUFS, PAIR, true>(ep, tmC, tmR, tmC16, M, N, row0, col0, taddr, tempty, cx, lane);
+  else if (MODE == EPI_F32_SCATTER) epilogue_scatter<HALF_N, STG_BUFS, PAIR>(ep, tmC, M, N, row0, col0, taddr, tempty, cx, lane);
   else epilogue_generic<HALF_N, PAIR>(ep, M, N, row0, col0, taddr, tempty, cx.stg, lane);
 }
 
@@ -1147,6 +1219,274 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Implicit-GEMM patch embedding: VisionTransformer.conv1 + positional embedding (clip/model.py:366, 412-416)
+// ---------------------------------------------------------------------------------------------
+// conv1 (kernel = stride = P, no bias) is the GEMM  x[b, 1 + t, :] = pixels(b, t)[3 P^2] . W[D, 3 P^2]^T + pos[1 + t]  over
+// M = batch * G^2 patches.  The A operand is never materialised: four producer warps (one thread per patch row of the
+// 128-row tile) read the pixels of their patch straight from the NCHW image — fp32 as the reference's transform hands it
+// over, or uint8 with ToTensor + Normalize applied on the fly — convert them to the 16-bit operand format and write them
+// into the 128B-swizzled K-major layout a TMA load would have produced; the weights arrive by TMA as usual.  Same
+// 128 x 256 tcgen05 main loop and scatter epilogue as gemm_tn_kernel<256, EPI_GENERIC>.
+//   uint8: v = (u8 / 255 - mean[c]) / std[c] with both IEEE divisions replaced by  q = a * r;  q += fma(-b, q, a) * r
+//   (r = RN(1 / b)): two FMAs instead of a division subroutine, bit-identical to the division for every (channel, byte)
+//   pair — which the host VERIFIES exhaustively (768 cases) for the mean / std of the call before it takes this path.
+struct PatchSrc {
+  const void* images;
+  int M, R, P, G, K;           // patches, resolution, patch size, grid, 3 P^2
+  int u8;
+  float mean[3], sd[3], rsd[3];
+};
+
+constexpr int PE_THREADS = 512;      // 4 control warps + 8 epilogue warps + 4 A-producer warps
+constexpr int PE_STAGES = 3;
+constexpr int PE_BLOCK_N = 256;
+constexpr uint32_t PE_A_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr uint32_t PE_B_BYTES = PE_BLOCK_N * BLOCK_K * 2;
+constexpr uint32_t PE_STAGE_BYTES = PE_A_BYTES + PE_B_BYTES;
+constexpr uint32_t PE_STG_BYTES = 8 * BOX_BYTES;
+constexpr uint32_t PE_BAR_BYTES = 8 * (2 * PE_STAGES + 4) + 16;
+constexpr uint32_t PE_KOFF_INVALID = 0xffffffffu;
+inline uint32_t pe_smem_bytes(int k_blocks) {
+  return PE_STAGES * PE_STAGE_BYTES + PE_STG_BYTES + PE_BAR_BYTES + static_cast<uint32_t>(k_blocks) * BLOCK_K * 4u + 1024u;
+}
+
+__device__ __forceinline__ float pe_norm_u8(float f, float mean, float sd, float rsd) {
+  constexpr float R255 = 1.0f / 255.0f;
+  float t = f * R255;
+  t = fmaf(fmaf(-255.0f, t, f), R255, t);          // RN(f / 255)
+  const float u = t - mean;
+  float y = u * rsd;
+  y = fmaf(fmaf(-sd, y, u), rsd, y);               // RN(u / sd)
+  return y;
+}
+
+template <bool U8, bool TMA_OUT>
+__global__ void __launch_bounds__(PE_THREADS, 1)
+patch_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC3, PatchSrc src, int N, int k_blocks,
+                   GemmEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
+  const uint32_t stg_base = smem_base + PE_STAGES * PE_STAGE_BYTES;
+  const uint32_t bar_base = stg_base + PE_STG_BYTES;
+  auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (PE_STAGES + s); };
+  auto tfull_bar = [&](uint32_t s) { return bar_base + 8u * (2 * PE_STAGES + s); };
+  auto tempty_bar = [&](uint32_t s) { return bar_base + 8u * (2 * PE_STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * PE_STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  // k -> (channel << 24 | element offset of pixel k inside the patch, relative to the patch origin in channel 0)
+  uint32_t* koff = reinterpret_cast<uint32_t*>(smem_gen + (bar_base + PE_BAR_BYTES - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int M = src.M;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (N + PE_BLOCK_N - 1) / PE_BLOCK_N;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    if (TMA_OUT) tma_prefetch_desc(&tmC3);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < PE_STAGES; ++s) {
+      mbar_init(full_bar(s), 1 + 4);   // the weight tile's expect_tx arrive + one arrive per A-producer warp
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  {
+    const int PP = src.P * src.P;
+    for (int k = threadIdx.x; k < k_blocks * BLOCK_K; k += PE_THREADS) {
+      uint32_t e = PE_KOFF_INVALID;
+      if (k < src.K) {
+        const int c = k / PP, rem = k - c * PP, i = rem / src.P, j = rem - i * src.P;
+        e = (static_cast<uint32_t>(c) << 24) | static_cast<uint32_t>((c * src.R + i) * src.R + j);
+      }
+      koff[k] = e;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer: weight tiles =====================
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % n_tiles;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(stage), PE_B_BYTES);
+          tma_load_2d(smem_base + stage * PE_STAGE_BYTES + PE_A_BYTES, &tmB, full_bar(stage), kb * BLOCK_K, n_blk * PE_BLOCK_N);
+        }
+        __syncwarp();
+        if (++stage == PE_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    const uint32_t idesc = umma_idesc_16b_f32(BLOCK_M, PE_BLOCK_N, ep.fp16);
+    uint32_t stage = 0, phase = 0, iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * PE_BLOCK_N;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_base + stage * PE_STAGE_BYTES;
+          const uint64_t a_desc = umma_desc_k_sw128(sa);
+          const uint64_t b_desc = umma_desc_k_sw128(sa + PE_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (kb == k_blocks - 1) umma_commit(tfull_bar(as));
+        }
+        __syncwarp();
+        if (++stage == PE_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===================== epilogue (8 warps): + positional embedding, scatter behind the CLS rows =====================
+    EpiCtx cx{0u, stg_base + (warp - 4) * BOX_BYTES, 0u, 0u, 0u};
+    uint32_t iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
+      epilogue_tile<PE_BLOCK_N, TMA_OUT ? EPI_F32_SCATTER : EPI_GENERIC, 1, false>(ep, &tmC3, &tmB, &tmB, M, N, m_blk * BLOCK_M, n_blk * PE_BLOCK_N,
+                                                                                  -1, 0, tmem_base + as * PE_BLOCK_N, tfull_bar(as), aphase,
+                                                                                  tempty_bar(as), cx, warp, lane);
+    }
+    if (TMA_OUT && lane == 0) tma_store_wait<0>();
+  } else if (warp >= 12) {
+    // ===================== A producers (4 warps): one thread per patch row of the tile =====================
+    // The pixels of a 16-byte operand unit (8 consecutive k) are 8 contiguous pixels of one image row (P % 8 == 0): one 8-byte
+    // (uint8) or two 16-byte (fp32) loads.  Loads run one GROUP ahead of the conversion — a group = the 8 units of a K block
+    // (uint8, 16 registers) or 4 of them (fp32, 32 registers) — and do not wait for the smem stage: only the stores do.
+    constexpr int CG = U8 ? 8 : 4, GROUPS = 8 / CG;       // units per group, groups per K block
+    using Raw = typename std::conditional<U8, uint2, float4>::type;
+    constexpr int RN = U8 ? 8 : 8;                        // registers-of-Raw per group (uint8: 8 x uint2, fp32: 4 x 2 float4)
+    const int r = threadIdx.x - 12 * 32;                  // 0 .. 127
+    const int GG = src.G * src.G;
+    struct It { int tile, kb, grp; long long base; bool valid, done; };
+    auto locate = [&](It& it) {
+      it.done = it.tile >= total_tiles;
+      it.valid = false;
+      it.base = 0;
+      if (it.done) return;
+      const int m = (it.tile / n_tiles) * BLOCK_M + r;
+      it.valid = m < M;
+      if (it.valid) {
+        const int b = m / GG, t = m - b * GG, py = t / src.G, px = t - py * src.G;
+        it.base = (static_cast<long long>(b) * 3 * src.R + static_cast<long long>(py) * src.P) * src.R + static_cast<long long>(px) * src.P;
+      }
+    };
+    auto advance = [&](It& it) {
+      if (++it.grp == GROUPS) {
+        it.grp = 0;
+        if (++it.kb == k_blocks) {
+          it.kb = 0;
+          it.tile += gridDim.x;
+          locate(it);
+        }
+      }
+    };
+    auto load_group = [&](const It& it, Raw (&buf)[RN], uint32_t& live) {
+      live = 0u;   // bit u: unit u of the group holds pixels (row inside the matrix, k below 3 P^2)
+#pragma unroll
+      for (int u = 0; u < CG; ++u) {
+        const uint32_t e0 = koff[it.kb * BLOCK_K + 8 * (it.grp * CG + u)];
+        if (it.valid && e0 != PE_KOFF_INVALID) {
+          live |= 1u << u;
+          const long long idx = it.base + (e0 & 0xffffffu);
+          if constexpr (U8) {
+            buf[u] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(src.images) + idx));
+          } else {
+            const float4* p4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src.images) + idx);
+            buf[2 * u] = __ldg(p4);
+            buf[2 * u + 1] = __ldg(p4 + 1);
+          }
+        }
+      }
+    };
+    uint32_t stage = 0, phase = 0;
+    It cur{static_cast<int>(blockIdx.x), 0, 0, 0, false, false};
+    locate(cur);
+    Raw bufA[RN], bufB[RN];
+    uint32_t liveA = 0u, liveB = 0u;
+    if (!cur.done) load_group(cur, bufA, liveA);
+    while (!cur.done) {
+      It nxt = cur;
+      advance(nxt);
+      if (!nxt.done) load_group(nxt, bufB, liveB);
+      if (cur.grp == 0) mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t row_addr = smem_base + stage * PE_STAGE_BYTES + static_cast<uint32_t>(r) * 128u;
+#pragma unroll
+      for (int u = 0; u < CG; ++u) {
+        float f[8];
+        if (liveA & (1u << u)) {
+          if constexpr (U8) {
+            const int c = static_cast<int>(koff[cur.kb * BLOCK_K + 8 * (cur.grp * CG + u)] >> 24);
+            const float mean = c == 0 ? src.mean[0] : c == 1 ? src.mean[1] : src.mean[2];
+            const float sd = c == 0 ? src.sd[0] : c == 1 ? src.sd[1] : src.sd[2];
+            const float rsd = c == 0 ? src.rsd[0] : c == 1 ? src.rsd[1] : src.rsd[2];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              f[e] = pe_norm_u8(static_cast<float>((bufA[u].x >> (8 * e)) & 0xffu), mean, sd, rsd);
+              f[4 + e] = pe_norm_u8(static_cast<float>((bufA[u].y >> (8 * e)) & 0xffu), mean, sd, rsd);
+            }
+          } else {
+            f[0] = bufA[2 * u].x; f[1] = bufA[2 * u].y; f[2] = bufA[2 * u].z; f[3] = bufA[2 * u].w;
+            f[4] = bufA[2 * u + 1].x; f[5] = bufA[2 * u + 1].y; f[6] = bufA[2 * u + 1].z; f[7] = bufA[2 * u + 1].w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
+        const uint32_t p0 = pack16x2(f[0], f[1], ep.fp16), p1 = pack16x2(f[2], f[3], ep.fp16);
+        const uint32_t p2 = pack16x2(f[4], f[5], ep.fp16), p3 = pack16x2(f[6], f[7], ep.fp16);
+        const uint32_t q = static_cast<uint32_t>(cur.grp * CG + u);
+        const uint32_t dst = row_addr + ((q ^ (static_cast<uint32_t>(r) & 7u)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+      }
+      if (cur.grp == GROUPS - 1) {
+        fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(stage));
+        if (++stage == PE_STAGES) { stage = 0; phase ^= 1u; }
+      }
+#pragma unroll
+      for (int i = 0; i < RN; ++i) bufA[i] = bufB[i];
+      liveA = liveB;
+      cur = nxt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
@@ -1165,6 +1505,9 @@ int build_maps(Maps& mp, const void* A, long long lda, const void* B, long long 
   mp.c16 = mp.a;
   if (mode == EPI_16 || mode == EPI_16_GELU || mode == EPI_16_LN || mode == EPI_16_GELU_LN) {
     rc = make_tmap_2d(&mp.c, ep.out, 2, M, N, ep.ldo, 32, 64);
+    if (rc) return rc;
+  } else if (mode == EPI_F32_SCATTER) {
+    rc = make_tmap_2d(&mp.c, ep.out, 4, static_cast<long long>(M / ep.row_grp) * (ep.row_grp + 1), N, ep.ldo, 32, 32);
     if (rc) return rc;
   } else if (mode == EPI_F32_RESID || mode == EPI_F32_RESID_EMIT) {
     rc = make_tmap_2d(&mp.c, ep.out, 4, M, N, ep.ldo, 32, 32);
@@ -1284,7 +1627,80 @@ int dispatch_tile(int bn, const void* A, long long lda, const void* B, long long
   return launch<128, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
 }
 
+
+// ToTensor + Normalize by multiply-and-correct equals the two IEEE divisions for every (channel, byte)?  768 cases.
+bool u8_norm_formula_exact(const float* mean_std) {
+  for (int c = 0; c < 3; ++c) {
+    const float mean = mean_std[c], sd = mean_std[3 + c], rsd = 1.0f / sd;
+    if (!(sd > 0.f)) return false;
+    for (int v = 0; v < 256; ++v) {
+      const float f = static_cast<float>(v);
+      volatile float t_ref = f / 255.0f;
+      volatile float u_ref = t_ref - mean;
+      volatile float y_ref = u_ref / sd;
+      const float r255 = 1.0f / 255.0f;
+      float t = f * r255;
+      t = fmaf(fmaf(-255.0f, t, f), r255, t);
+      const float u = t - mean;
+      float y = u * rsd;
+      y = fmaf(fmaf(-sd, y, u), rsd, y);
+      if (memcmp(&y, const_cast<const float*>(&y_ref), sizeof(float)) != 0) return false;
+    }
+  }
+  return true;
+}
+
 }  // namespace
+
+int patch_embed(const void* images, int u8, const float* mean_std, int batch, int R, int P, const void* conv_w, int k_pad,
+                const float* pos, float* x, int D, int fp16, cudaStream_t stream) {
+  OVMR_REQUIRE(images && conv_w && pos && x, "patch_embed: null argument");
+  OVMR_REQUIRE(batch > 0 && P > 0 && R >= P && D % 8 == 0, "patch_embed: bad geometry batch=%d R=%d P=%d D=%d", batch, R, P, D);
+  OVMR_REQUIRE(P % 8 == 0 && R % 8 == 0, "patch_embed: patch size and resolution must be multiples of 8 (P=%d R=%d): the 14-pixel "
+               "patches of ViT-L/14 go through ovmr_patchify + ovmr_gemm_tn", P, R);
+  const int G = R / P, K = 3 * P * P;
+  OVMR_REQUIRE(k_pad >= K && k_pad % 8 == 0, "patch_embed: k_pad=%d must be >= %d and a multiple of 8", k_pad, K);
+  OVMR_REQUIRE(static_cast<long long>(batch) * G * G < (1LL << 31) && 3LL * R * R < (1 << 24), "patch_embed: problem too large");
+  OVMR_REQUIRE((reinterpret_cast<uintptr_t>(images) & (u8 ? 7 : 31)) == 0, "patch_embed: images must be %d-byte aligned", u8 ? 8 : 32);
+  PatchSrc src;
+  src.images = images; src.M = batch * G * G; src.R = R; src.P = P; src.G = G; src.K = K; src.u8 = u8;
+  for (int c = 0; c < 3; ++c) {
+    src.mean[c] = u8 ? mean_std[c] : 0.f;
+    src.sd[c] = u8 ? mean_std[3 + c] : 1.f;
+    src.rsd[c] = 1.0f / src.sd[c];
+  }
+  const int k_blocks = (k_pad + BLOCK_K - 1) / BLOCK_K;
+  const uint32_t smem = pe_smem_bytes(k_blocks);
+  OVMR_REQUIRE(smem <= 232448u, "patch_embed: patch too large for the offset table (k_pad=%d)", k_pad);
+  CUtensorMap tmB;
+  int rc = make_tmap_16b(&tmB, conv_w, D, k_pad, k_pad, PE_BLOCK_N);
+  if (rc) return rc;
+  GemmEpilogue ep;
+  ep.resid = pos; ep.ldr = D; ep.out = x; ep.ldo = D; ep.out_bf16 = 0; ep.row_grp = G * G; ep.fp16 = fp16;
+  const bool tma_out = G * G >= 32 && D % 32 == 0;
+  CUtensorMap tmC3 = tmB;
+  if (tma_out) {
+    rc = make_tmap_2d(&tmC3, x, 4, static_cast<long long>(batch) * (G * G + 1), D, D, 32, 32);
+    if (rc) return rc;
+  }
+  static PerDeviceOnce attr;
+  if (attr.first()) {
+    OVMR_CHECK_CUDA(cudaFuncSetAttribute(patch_embed_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    OVMR_CHECK_CUDA(cudaFuncSetAttribute(patch_embed_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    OVMR_CHECK_CUDA(cudaFuncSetAttribute(patch_embed_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    OVMR_CHECK_CUDA(cudaFuncSetAttribute(patch_embed_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  }
+  const int total = ((src.M + BLOCK_M - 1) / BLOCK_M) * ((D + PE_BLOCK_N - 1) / PE_BLOCK_N);
+  const int grid = total < num_sms() ? total : num_sms();
+  ProfScope prof(PROF_GEMM, 2.0 * src.M * D * K, stream);
+  auto kern = u8 ? (tma_out ? patch_embed_kernel<true, true> : patch_embed_kernel<true, false>)
+                 : (tma_out ? patch_embed_kernel<false, true> : patch_embed_kernel<false, false>);
+  OVMR_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(PE_THREADS), smem, stream, tmB, tmC3, src, D, k_blocks, ep));
+  count_launches(1);
+  return 0;
+}
+
+bool patch_embed_u8_exact(const float* mean_std) { return mean_std != nullptr && u8_norm_formula_exact(mean_std); }
 
 size_t gemm_ln_scratch_counter_offset(long long M, int N) {
   const long long m_pad = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (2 * BLOCK_M);
@@ -1378,6 +1794,10 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, i
     return launch_rowln<4, false, 2>(A, lda, B, ldb, M, N, K, ep, stream);
   }
   if (tma_resid) return dispatch_tile<EPI_F32_RESID>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+  static const bool tma_scatter = [] { const char* e = getenv("OVMR_TMA_SCATTER"); return e == nullptr || e[0] != '0'; }();
+  if (tma_scatter && ep.row_grp >= 32 && M % ep.row_grp == 0 && ep.resid != nullptr && ep.bias == nullptr && ep.act == 0 &&
+      ep.alpha == 1.0f && N % 32 == 0 && ep.ldo % 4 == 0 && ep.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0)
+    return dispatch_tile<EPI_F32_SCATTER>(bn, A, lda, B, ldb, M, N, K, ep, stream);
   return dispatch_tile<EPI_GENERIC>(bn, A, lda, B, ldb, M, N, K, ep, stream);
 }
 

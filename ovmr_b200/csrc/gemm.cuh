@@ -73,4 +73,14 @@ size_t gemm_ln_scratch_counter_bytes(long long M);
 int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                  const GemmEpilogue& ep, cudaStream_t stream, int force_block_n = 0);
 
+// VisionTransformer.conv1 + positional embedding as an implicit GEMM (clip/model.py:366, 412-416): the patch rows are read
+// from the NCHW images (fp32, or uint8 with ToTensor + Normalize on the fly: mean_std = HOST pointer to mean RGB, std RGB) by
+// the kernel's producer warps; x fp32 [batch * (G*G + 1), D] receives patch t of image b at row b * (G*G + 1) + 1 + t
+// (the CLS rows are not touched).  conv_w: 16-bit [D, k_pad], zero padded.
+int patch_embed(const void* images, int u8, const float* mean_std, int batch, int R, int P, const void* conv_w, int k_pad,
+                const float* pos, float* x, int D, int fp16, cudaStream_t stream);
+// true when the producer's multiply-and-correct normalisation is bit-identical to (u8 / 255 - mean) / std for all 768
+// (channel, byte) pairs of this mean / std (checked on the host); otherwise callers use patchify_u8 + gemm_tn.
+bool patch_embed_u8_exact(const float* mean_std);
+
 }  // namespace ovmr

@@ -289,6 +289,61 @@ def test_patchify_u8_matches_totensor_normalize_bit_exact(B, R, P):
     assert (out.cpu()[:, k:] == 0).all()
 
 
+@pytest.mark.parametrize("B,R,P,D", [(3, 64, 16, 128), (40, 224, 16, 768), (7, 224, 16, 1024), (2, 64, 8, 512), (5, 224, 32, 768)])
+@pytest.mark.parametrize("u8", [0, 1])
+@pytest.mark.parametrize("fp16", [0, 1])
+def test_patch_embed_implicit_gemm(B, R, P, D, u8, fp16):
+    """VisionTransformer.conv1 + positional embedding (clip/model.py:366, 412-416) as an implicit GEMM — producer warps read
+    the patches from the NCHW image, uint8 pixels normalised on the fly without divisions — against (a) the fp32 conv of the
+    16-bit-rounded operands and (b) the explicit form it replaces (patchify / patchify_u8 + the scatter GEMM with the same
+    128 x 256 tiles): same operand bits, same K order, so the rows must be IDENTICAL.  CLS rows are not touched."""
+    import ctypes as C
+    L, lib = _lib()
+    t16 = torch.float16 if fp16 else torch.bfloat16
+    g = torch.Generator().manual_seed(B + R + P + D + u8)
+    G = R // P
+    k = 3 * P * P
+    kpad = (k + 7) // 8 * 8
+    mean = torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(1, 3, 1, 1)
+    std = torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(1, 3, 1, 1)
+    ms = (C.c_float * 6)(*(mean.flatten().tolist() + std.flatten().tolist()))
+    if u8:
+        raw = torch.randint(0, 256, (B, 3, R, R), generator=g, dtype=torch.uint8)
+        img = raw.float().div(255).sub(mean).div(std)
+    else:
+        raw = img = torch.randn(B, 3, R, R, generator=g)
+    w = torch.randn(D, 3, P, P, generator=g) * 0.03
+    pos = torch.randn(G * G + 1, D, generator=g)
+    wp = torch.zeros(D, kpad)
+    wp[:, :k] = w.reshape(D, k)
+    RAW, W16, POS = raw.to(DEV).contiguous(), wp.to(DEV).to(t16).contiguous(), pos.to(DEV).contiguous()
+    x = torch.full((B * (G * G + 1), D), -7.0, device=DEV)
+    L.check(lib.ovmr_patch_embed(RAW.data_ptr(), u8, ms, B, R, P, W16.data_ptr(), kpad, POS.data_ptr(), x.data_ptr(), D, fp16,
+                                 L.stream()))
+    torch.cuda.synchronize()
+    xv = x.view(B, G * G + 1, D)
+    assert (xv[:, 0] == -7.0).all(), "CLS rows must not be written"
+    # (a) conv of the rounded operands in fp32
+    ref = torch.nn.functional.conv2d(img.to(t16).float(), w.to(t16).float(), stride=P)          # [B, D, G, G]
+    ref = ref.reshape(B, D, G * G).permute(0, 2, 1) + pos[1:].unsqueeze(0)
+    err = (xv[:, 1:].cpu() - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
+    # (b) the explicit form: patch matrix in HBM + scatter GEMM on 128 x 256 tiles
+    patches = torch.empty(B * G * G, kpad, dtype=t16, device=DEV)
+    if u8:
+        L.check(lib.ovmr_patchify_u8(RAW.data_ptr(), ms, patches.data_ptr(), B, R, P, kpad, fp16, L.stream()))
+    else:
+        L.check(lib.ovmr_patchify(RAW.data_ptr(), patches.data_ptr(), B, R, P, kpad, fp16, L.stream()))
+    x2 = torch.full_like(x, -7.0)
+    L.check(lib.ovmr_gemm_tn(patches.data_ptr(), kpad, W16.data_ptr(), kpad, B * G * G, D, kpad, None, POS.data_ptr(), D,
+                             x2.data_ptr(), D, 0, 0, 1.0, G * G, 256 if D >= 256 else 128, fp16, L.stream()))
+    torch.cuda.synchronize()
+    if D >= 256:
+        assert torch.equal(x, x2), (x - x2).abs().max().item()
+    else:
+        assert (x - x2).abs().max() < 1e-5
+
+
 def test_l2norm_split_mean():
     L, lib = _lib()
     g = torch.Generator().manual_seed(3)

@@ -27,3 +27,34 @@ img = torch.randn(B, 3, 224, 224, device=dev)
 p = torch.empty(B * 196, 768, device=dev, dtype=torch.bfloat16)
 ms = timeit(lambda: L.check(lib.ovmr_patchify(img.data_ptr(), p.data_ptr(), B, 224, 16, 768, 0, L.stream())))
 print(f"patchify B=256: {ms*1e3:.1f} us  {B*3*224*224*6/ms/1e6:.0f} GB/s")
+# patch embedding at the bench batch: explicit (patchify_u8 + scatter GEMM) against the implicit GEMM
+import ctypes as C
+for (Bp, R, P, Dp) in ((512, 224, 16, 768), (512, 224, 32, 768)):
+    G = R // P; k = 3 * P * P; kpad = (k + 7) // 8 * 8
+    u8 = torch.randint(0, 256, (Bp, 3, R, R), device=dev, dtype=torch.uint8)
+    f32 = torch.randn(Bp, 3, R, R, device=dev)
+    w = (torch.randn(Dp, kpad, device=dev) * 0.03).bfloat16()
+    pos = torch.randn(G * G + 1, Dp, device=dev)
+    xx = torch.empty(Bp * (G * G + 1), Dp, device=dev)
+    pt = torch.empty(Bp * G * G, kpad, device=dev, dtype=torch.bfloat16)
+    ms_ = (C.c_float * 6)(0.48145466, 0.4578275, 0.40821073, 0.26862954, 0.26130258, 0.27577711)
+    def explicit_u8():
+        L.check(lib.ovmr_patchify_u8(u8.data_ptr(), ms_, pt.data_ptr(), Bp, R, P, kpad, 0, L.stream()))
+        L.check(lib.ovmr_gemm_tn(pt.data_ptr(), kpad, w.data_ptr(), kpad, Bp * G * G, Dp, kpad, None, pos.data_ptr(), Dp, xx.data_ptr(), Dp, 0, 0, 1.0, G * G, 0, 0, L.stream()))
+    def explicit_f32():
+        L.check(lib.ovmr_patchify(f32.data_ptr(), pt.data_ptr(), Bp, R, P, kpad, 0, L.stream()))
+        L.check(lib.ovmr_gemm_tn(pt.data_ptr(), kpad, w.data_ptr(), kpad, Bp * G * G, Dp, kpad, None, pos.data_ptr(), Dp, xx.data_ptr(), Dp, 0, 0, 1.0, G * G, 0, 0, L.stream()))
+    imp_u8 = lambda: L.check(lib.ovmr_patch_embed(u8.data_ptr(), 1, ms_, Bp, R, P, w.data_ptr(), kpad, pos.data_ptr(), xx.data_ptr(), Dp, 0, L.stream()))
+    imp_f32 = lambda: L.check(lib.ovmr_patch_embed(f32.data_ptr(), 0, ms_, Bp, R, P, w.data_ptr(), kpad, pos.data_ptr(), xx.data_ptr(), Dp, 0, L.stream()))
+    t = [timeit(f, 50) * 1e3 for f in (explicit_u8, imp_u8, explicit_f32, imp_f32)]
+    print(f"patch-embed B={Bp} R={R} P={P} D={Dp}: uint8 explicit {t[0]:.1f} us, implicit {t[1]:.1f} us | fp32 explicit {t[2]:.1f} us, implicit {t[3]:.1f} us", flush=True)
+# the scatter GEMM alone (patch matrix already in HBM): CTA-pair kernel against the 1-CTA 128 x 256 kernel the implicit form is built on
+Bp, R, P, Dp = 512, 224, 16, 768
+G = R // P; k = 3 * P * P; kpad = k
+w = (torch.randn(Dp, kpad, device=dev) * 0.03).bfloat16(); pos = torch.randn(G * G + 1, Dp, device=dev)
+xx = torch.empty(Bp * (G * G + 1), Dp, device=dev); pt = torch.randn(Bp * G * G, kpad, device=dev).bfloat16()
+for bn in (0, 256, 128):
+    ms = timeit(lambda: L.check(lib.ovmr_gemm_tn(pt.data_ptr(), kpad, w.data_ptr(), kpad, Bp * G * G, Dp, kpad, None, pos.data_ptr(), Dp, xx.data_ptr(), Dp, 0, 0, 1.0, G * G, bn, 0, L.stream())), 50)
+    print(f"scatter GEMM alone, block_n={bn}: {ms*1e3:.1f} us", flush=True)
+ms = timeit(lambda: L.check(lib.ovmr_gemm_tn(pt.data_ptr(), kpad, w.data_ptr(), kpad, Bp * G * G, Dp, kpad, None, None, 0, xx.data_ptr(), Dp, 0, 0, 1.0, 0, 256, 0, L.stream())), 50)
+print(f"plain fp32-out GEMM (no scatter, no residual), block_n=256: {ms*1e3:.1f} us", flush=True)
