@@ -234,6 +234,17 @@ int ovmr_split_bf16(const float* x, long long rows, int width, void* out, int or
 int ovmr_fusion_softmax_topk(const float* logits, long long rows, long long ld, int seg_stride, int nseg, int n_cls,
                              const float* fusion_w, float* probs, long long ldp, int k, int* top_idx,
                              float* top_val, void* stream);
+/* The eval branch of CustomCLIP.forward (trainers/mm_classifier_one_prompt.py:348-363) + the evaluator's top-k
+ * (dassl/evaluation/evaluator.py:54-58) as ONE kernel: logits = logit_scale * feats @ W_s^T for s in (mm, v, t), three softmaxes
+ * over the classes, p[q, c] = sum_s fusion_w[c, s] * softmax_s[q, c] (nseg = 1: plain softmax), top-k with ties -> lowest index.
+ * The logits are never written: a CTA owns 128 query rows and sweeps the classes twice on the tensor core (statistics, then
+ * emit).  feats_split = ovmr_split_bf16(feats, order 0) [rows, operand_width = 3E]; bank_class_major =
+ * ovmr_split_bf16(classifier rows, order 1) with row c * nseg + s holding classifier s of class c.  probs (fp32 [rows, ldp])
+ * and / or top-k (k <= 8) are produced; no limit on n_cls.  ovmr_gemm_tn + ovmr_fusion_softmax_topk remain as the explicit form. */
+int ovmr_head_fused(const void* feats_split, long long rows, const void* bank_class_major, int n_cls, int nseg,
+                    int operand_width, float logit_scale, const float* fusion_w, float* probs, long long ldp, int k,
+                    int* top_idx, float* top_val, void* stream);
+
 /* argmax per (row, classifier segment), ties -> lowest index (trainers/...:268-270 via torcheval). */
 int ovmr_argmax_segments(const float* logits, long long rows, long long ld, int seg_stride, int nseg, int n_cls,
                          int* pred, void* stream);

@@ -498,6 +498,13 @@ int ovmr_fusion_softmax_topk(const float* logits, long long rows, long long ld, 
                                    S(stream));
 }
 
+int ovmr_head_fused(const void* feats_split, long long rows, const void* bank_class_major, int n_cls, int nseg, int operand_width,
+                    float logit_scale, const float* fusion_w, float* probs, long long ldp, int k, int* top_idx, float* top_val,
+                    void* stream) {
+  return ovmr::head_fused(feats_split, rows, bank_class_major, n_cls, nseg, operand_width, logit_scale, fusion_w, probs, ldp, k,
+                          top_idx, top_val, S(stream));
+}
+
 int ovmr_argmax_segments(const float* logits, long long rows, long long ld, int seg_stride, int nseg, int n_cls, int* pred,
                          void* stream) {
   return ovmr::argmax_segments(logits, rows, ld, seg_stride, nseg, n_cls, pred, S(stream));

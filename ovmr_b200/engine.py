@@ -294,6 +294,26 @@ class ClassifierBank:
             L.check(lib.ovmr_split_bf16(w.data_ptr(), self.C, self.E, self.packed[s * self.Cpad:].data_ptr(), 1,
                                         self.Cpad, L.stream()), "ovmr_split_bf16")
 
+    def class_major(self) -> torch.Tensor:
+        """The same operand rows reordered class-major — row c * nseg + s — as ovmr_head_fused wants them: the three
+        logits of a class are then adjacent accumulator columns of one thread.  Built once per bank (a row permutation of
+        `packed`, at classifier-generation time, not on the classification loop)."""
+        il = getattr(self, "_class_major", None)
+        if il is None:
+            v = self.packed.view(self.nseg, self.Cpad, 3 * self.E)[:, :self.C]
+            il = v.permute(1, 0, 2).reshape(self.C * self.nseg, 3 * self.E).contiguous()
+            self._class_major = il
+        return il
+
+    def split_feats(self, feats: torch.Tensor) -> torch.Tensor:
+        """feats fp32 [R, E] -> bf16 [R, 3E] hi / hi / lo (A operand of the logit GEMM)."""
+        lib = L.lib()
+        feats = feats.to(F32).contiguous()
+        R = feats.shape[0]
+        a = torch.empty(R, 3 * self.E, dtype=BF16, device=feats.device)
+        L.check(lib.ovmr_split_bf16(feats.data_ptr(), R, self.E, a.data_ptr(), 0, R, L.stream()), "ovmr_split_bf16")
+        return a
+
     def logits(self, feats: torch.Tensor, scale: float) -> torch.Tensor:
         """feats fp32 [R, E] -> fp32 [R, nseg*Cpad] = scale * feats @ W_s^T for every segment."""
         lib = L.lib()
@@ -309,6 +329,12 @@ class ClassifierBank:
         return out
 
 
+def fused_head_enabled() -> bool:
+    """OVMR_FUSED_HEAD=0 selects the explicit head (logit GEMM -> fp32 logits in HBM -> fusion_softmax_topk kernel)."""
+    import os
+    return os.environ.get("OVMR_FUSED_HEAD", "1") != "0"
+
+
 def classify(bank: ClassifierBank, feats: torch.Tensor, scale: float, fusion_w: Optional[torch.Tensor], k: int = 1,
              want_probs: bool = True, chunk: int = 8192):
     """softmax (nseg=1) or 3-way fusion softmax over classes + top-k.  Returns (probs|None, idx[R,k], val[R,k])."""
@@ -319,6 +345,13 @@ def classify(bank: ClassifierBank, feats: torch.Tensor, scale: float, fusion_w: 
     idx = torch.empty(R, max(k, 1), dtype=I32, device=dev)
     val = torch.empty(R, max(k, 1), dtype=F32, device=dev)
     fw = None if fusion_w is None else fusion_w.to(F32).contiguous()
+    if fused_head_enabled() and k <= 8 and scale > 0:
+        # one kernel: logit GEMM + softmaxes + fusion + top-k; the [R, nseg * C] logits are never written
+        a = bank.split_feats(feats)
+        L.check(lib.ovmr_head_fused(a.data_ptr(), R, bank.class_major().data_ptr(), bank.C, bank.nseg, 3 * bank.E, float(scale),
+                                    L.ptr(fw), L.ptr(probs), bank.C, k, idx.data_ptr(), val.data_ptr(), L.stream()),
+                "ovmr_head_fused")
+        return probs, idx[:, :k], val[:, :k]
     for r0 in range(0, R, chunk):
         r = min(chunk, R - r0)
         lg = bank.logits(feats[r0:r0 + r], scale)

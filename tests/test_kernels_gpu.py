@@ -400,6 +400,97 @@ def test_fusion_softmax_topk(R, Cn, k):
     assert (p1.cpu() - torch.softmax(segs[0], -1)).abs().max() < 2e-6
 
 
+def _split_operands(feats, classifiers):
+    """feats fp32 [R, E], classifiers list of fp32 [C, E] -> (A bf16 [R, 3E], bank bf16 [C * nseg, 3E] class-major) on DEV."""
+    L, lib = _lib()
+    R, E = feats.shape
+    Cn, nseg = classifiers[0].shape[0], len(classifiers)
+    F = feats.to(DEV).contiguous()
+    a = torch.empty(R, 3 * E, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.ovmr_split_bf16(F.data_ptr(), R, E, a.data_ptr(), 0, R, L.stream()))
+    rows = torch.stack(classifiers, 1).reshape(Cn * nseg, E).to(DEV).contiguous()       # row c * nseg + s
+    bank = torch.empty(Cn * nseg, 3 * E, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.ovmr_split_bf16(rows.data_ptr(), Cn * nseg, E, bank.data_ptr(), 1, Cn * nseg, L.stream()))
+    return a, bank
+
+
+@pytest.mark.parametrize("R,Cn,E,k", [(64, 10, 128, 1), (300, 1000, 512, 5), (130, 1203, 512, 8), (40, 21841, 512, 3), (257, 65, 768, 5)])
+@pytest.mark.parametrize("nseg", [3, 1])
+def test_head_fused_kernel(R, Cn, E, k, nseg):
+    """Eval branch of CustomCLIP.forward + evaluator top-k as ONE kernel (trainers/mm_classifier_one_prompt.py:348-363,
+    dassl/evaluation/evaluator.py:54-58): logits never written, two tensor-core sweeps over the classes.  Checked against the
+    fp64 formula on the same L2-normalised operands (probabilities within 2e-6: they are ~1/C, logits carry the hi / lo split's
+    2^-16), against the explicit head (GEMM + fusion_softmax_topk) and for self-consistency: top-k == top-k of the emitted
+    probabilities, ties -> lowest index; top-k-only mode (no probability matrix) returns the same lists."""
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(R + Cn + E + nseg)
+    nrm = torch.nn.functional.normalize
+    feats = nrm(torch.randn(R, E, generator=g), dim=-1)
+    cls = [nrm(torch.randn(Cn, E, generator=g) + 0.5 * s, dim=-1) for s in range(nseg)]
+    cls[0][: min(Cn, R)] = nrm(cls[0][: min(Cn, R)] + 0.6 * feats[: min(Cn, R)], dim=-1)      # some confident rows
+    fw = torch.softmax(torch.randn(Cn, 3, generator=g), -1)
+    scale = 100.0
+    a, bank = _split_operands(feats, cls)
+    FW = fw.to(DEV).contiguous()
+    probs = torch.full((R, Cn), -1.0, device=DEV)
+    idx = torch.full((R, k), -7, dtype=torch.int32, device=DEV)
+    val = torch.empty(R, k, device=DEV)
+    L.check(lib.ovmr_head_fused(a.data_ptr(), R, bank.data_ptr(), Cn, nseg, 3 * E, scale, FW.data_ptr() if nseg == 3 else None,
+                                probs.data_ptr(), Cn, k, idx.data_ptr(), val.data_ptr(), L.stream()))
+    torch.cuda.synchronize()
+    sm = [torch.softmax(scale * feats.double() @ w.double().t(), -1) for w in cls]
+    ref = sum(sm[s] * fw[:, s].double() for s in range(3)) if nseg == 3 else sm[0]
+    assert (probs.cpu().double() - ref).abs().max() < 2e-6 + 2e-3 * ref.max().item()    # (logit error <= scale * 2^-17 in the worst case)
+    oi, ov = O.topk(probs.cpu(), k)
+    assert torch.equal(idx.cpu().long(), oi)
+    assert torch.equal(val.cpu(), ov)
+    # top-k only: same lists, nothing else written
+    idx2 = torch.full((R, k), -7, dtype=torch.int32, device=DEV)
+    val2 = torch.empty(R, k, device=DEV)
+    L.check(lib.ovmr_head_fused(a.data_ptr(), R, bank.data_ptr(), Cn, nseg, 3 * E, scale, FW.data_ptr() if nseg == 3 else None,
+                                None, 0, k, idx2.data_ptr(), val2.data_ptr(), L.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(idx2, idx) and torch.equal(val2, val)
+    # explicit head on the same operands (segment-major bank, logits in HBM)
+    Cpad = (Cn + 7) // 8 * 8
+    seg_bank = torch.zeros(nseg * Cpad, 3 * E, dtype=torch.bfloat16, device=DEV)
+    seg_bank.view(nseg, Cpad, 3 * E)[:, :Cn] = bank.view(Cn, nseg, 3 * E).permute(1, 0, 2)
+    lg = torch.empty(R, nseg * Cpad, device=DEV)
+    L.check(lib.ovmr_gemm_tn(a.data_ptr(), 3 * E, seg_bank.data_ptr(), 3 * E, R, nseg * Cpad, 3 * E, None, None, 0, lg.data_ptr(),
+                             nseg * Cpad, 0, 0, scale, 0, 0, 0, L.stream()))
+    p3 = torch.empty(R, Cn, device=DEV)
+    i3 = torch.empty(R, k, dtype=torch.int32, device=DEV)
+    v3 = torch.empty(R, k, device=DEV)
+    L.check(lib.ovmr_fusion_softmax_topk(lg.data_ptr(), R, nseg * Cpad, Cpad, nseg, Cn, FW.data_ptr() if nseg == 3 else None,
+                                         p3.data_ptr(), Cn, k, i3.data_ptr(), v3.data_ptr(), L.stream()))
+    torch.cuda.synchronize()
+    assert (probs - p3).abs().max() < 2e-6 + 2e-4 * float(p3.max())
+    decided = (v3[:, :1] - p3.topk(min(k + 1, Cn), -1).values[:, -1:]) > 1e-5     # rows whose k-th / (k+1)-th gap is not a rounding tie
+    assert torch.equal(idx[decided.squeeze(1)][:, 0], i3[decided.squeeze(1)][:, 0])
+
+
+def test_head_fused_ties_and_nan_rows():
+    """Ties -> lowest class index; a NaN feature row gives NaN probabilities and in-range top-k indices."""
+    L, lib = _lib()
+    E, Cn = 64, 20
+    feats = torch.zeros(4, E)
+    feats[:, 0] = 1.0
+    cls = torch.zeros(Cn, E)
+    cls[:, 1] = 1.0                                   # all classes orthogonal to the queries: every logit equal
+    cls[3, 0] = cls[5, 0] = 0.5                       # two equal winners
+    feats[2] = float("nan")
+    a, bank = _split_operands(feats, [cls])
+    probs = torch.empty(4, Cn, device=DEV)
+    idx = torch.full((4, 2), -7, dtype=torch.int32, device=DEV)
+    val = torch.empty(4, 2, device=DEV)
+    L.check(lib.ovmr_head_fused(a.data_ptr(), 4, bank.data_ptr(), Cn, 1, 3 * E, 10.0, None, probs.data_ptr(), Cn, 2, idx.data_ptr(),
+                                val.data_ptr(), L.stream()))
+    torch.cuda.synchronize()
+    assert idx[0].tolist() == [3, 5] and idx[1].tolist() == [3, 5] and idx[3].tolist() == [3, 5]
+    assert bool(torch.isnan(probs[2]).all()) and bool(((idx[2] >= 0) & (idx[2] < Cn)).all()) and bool(torch.isnan(val[2]).all())
+    assert bool(torch.isfinite(probs[[0, 1, 3]]).all())
+
+
 def test_topk_ties_lowest_index():
     L, lib = _lib()
     logits = torch.zeros(4, 24)

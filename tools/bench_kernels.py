@@ -58,3 +58,18 @@ for bn in (0, 256, 128):
     print(f"scatter GEMM alone, block_n={bn}: {ms*1e3:.1f} us", flush=True)
 ms = timeit(lambda: L.check(lib.ovmr_gemm_tn(pt.data_ptr(), kpad, w.data_ptr(), kpad, Bp * G * G, Dp, kpad, None, None, 0, xx.data_ptr(), Dp, 0, 0, 1.0, 0, 256, 0, L.stream())), 50)
 print(f"plain fp32-out GEMM (no scatter, no residual), block_n=256: {ms*1e3:.1f} us", flush=True)
+# classification head: explicit (split + logit GEMM + fusion_softmax_topk, chunks of 8192 rows) against the fused kernel
+from ovmr_b200 import engine as Eng
+import os
+for (Q, Cn) in ((50000, 1000), (8192, 21841)):
+    nrm = torch.nn.functional.normalize
+    feats = nrm(torch.randn(Q, 512, device=dev), dim=-1)
+    bank = Eng.ClassifierBank([nrm(torch.randn(Cn, 512, device=dev), dim=-1) for _ in range(3)])
+    fw = torch.softmax(torch.randn(Cn, 3, device=dev), -1)
+    res = []
+    for mode in ("0", "1"):
+        os.environ["OVMR_FUSED_HEAD"] = mode
+        for want in (False, True):
+            res.append(timeit(lambda: Eng.classify(bank, feats, 100.0, fw, k=5, want_probs=want), 10) * 1e3)
+    print(f"head Q={Q} C={Cn}: explicit top-5 {res[0]:.0f} us, with probabilities {res[1]:.0f} us | fused top-5 {res[2]:.0f} us, with probabilities {res[3]:.0f} us", flush=True)
+os.environ.pop("OVMR_FUSED_HEAD", None)
