@@ -571,8 +571,8 @@ def main():
     q_dev = device_images(n_q_local, res, device, seed=1001 + rank)
     ex_labels = torch.arange(shard.lo, shard.hi, device=device).repeat_interleave(S)
 
-    ex_plan = [(o * S, z * S) for o, z in plan_batches(shard.size, cls_per_batch, unit=S, tokens_per_image=tokens)]
-    q_plan = plan_batches(n_q_local, B, tokens_per_image=tokens)
+    ex_plan = [(o * S, z * S) for o, z in plan_batches(shard.size, cls_per_batch, unit=S, tokens_per_image=tokens, width=arch[3])]
+    q_plan = plan_batches(n_q_local, B, tokens_per_image=tokens, width=arch[3])
 
     def exemplar_batches(images, labels):
         return [{"img": images[o:o + z], "label": labels[o:o + z]} for o, z in ex_plan]

@@ -11,21 +11,26 @@ from typing import Dict, Iterable, Iterator, List, Tuple
 import torch
 
 
-def plan_batches(n: int, cap: int, unit: int = 1, tokens_per_image: int = 197, sm_pairs: int = 74) -> List[Tuple[int, int]]:
+def plan_batches(n: int, cap: int, unit: int = 1, tokens_per_image: int = 197, sm_pairs: int = 74, width: int = 768,
+                 ln_groups: int = 22) -> List[Tuple[int, int]]:
     """Split n items (each `unit` images) into batches of at most `cap` items; returns (offset, size) pairs.
     Two candidates — full batches plus a ragged tail, or ceil(n / cap) batches whose sizes differ by at most one —
-    are compared with a wave model of the persistent CTA-pair GEMMs (256 x 256 tiles over `sm_pairs` SM pairs; QKV /
-    out-proj / c_fc / c_proj of ViT-B/16) and the cheaper one is used: a ragged tail costs whole waves, a slightly
-    short batch may too."""
+    are compared with a wave model of the persistent GEMMs of one layer (256 x 256 tiles; QKV and c_fc over `sm_pairs` CTA
+    pairs, the LayerNorm-emitting out-proj / c_proj over `ln_groups` row-block clusters when width <= 768 — 22 clusters of 6 CTAs
+    fit a B200 — else over the pairs as well; c_proj weighs 4 K-lengths) and the cheaper one is used: a ragged tail costs whole
+    waves, a slightly short batch may too."""
     if n <= 0:
         return []
     cap = max(1, cap)
+    nt = max(1, width // 256)
 
     def cost(sizes):
         c = 0
         for z in sizes:
             mp = -(-z * unit * tokens_per_image // 256)
-            c += sum(-(-mp * nt // sm_pairs) * k for nt, k in ((9, 1), (3, 1), (12, 1), (3, 4)))
+            c += -(-mp * 3 * nt // sm_pairs) + -(-mp * 4 * nt // sm_pairs)                 # QKV, c_fc
+            resid = -(-mp // ln_groups) if width <= 768 else -(-mp * nt // sm_pairs)        # one wave = one row block per cluster
+            c += resid * (1 + 4)                                                            # out-proj (K = D) + c_proj (K = 4 D)
         return c
     k = -(-n // cap)
     base, extra = divmod(n, k)
