@@ -244,6 +244,11 @@ int ovmr_fusion_softmax_topk(const float* logits, long long rows, long long ld, 
 int ovmr_head_fused(const void* feats_split, long long rows, const void* bank_class_major, int n_cls, int nseg,
                     int operand_width, float logit_scale, const float* fusion_w, float* probs, long long ldp, int k,
                     int* top_idx, float* top_val, void* stream);
+/* The exemplar self-classification of forward_prompt (trainers/mm_classifier_one_prompt.py:263-270: pred = argmax of each
+ * classifier's logits, input of multiclass_f1_score) from the same operands in ONE sweep: pred int32 [rows, nseg],
+ * ties -> lowest index.  The [C S, 3 C] logits the reference materialises (22.9 GB at 21,841 classes x 4 shots) never exist. */
+int ovmr_head_fused_argmax(const void* feats_split, long long rows, const void* bank_class_major, int n_cls, int nseg,
+                           int operand_width, int* pred, void* stream);
 
 /* argmax per (row, classifier segment), ties -> lowest index (trainers/...:268-270 via torcheval). */
 int ovmr_argmax_segments(const float* logits, long long rows, long long ld, int seg_stride, int nseg, int n_cls,

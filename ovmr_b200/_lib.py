@@ -85,6 +85,7 @@ SIGNATURES = {
                                          c_void_p, c_void_p, c_void_p]),
     "ovmr_head_fused": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_ll, c_int, c_void_p,
                                 c_void_p, c_void_p]),
+    "ovmr_head_fused_argmax": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ovmr_argmax_segments": (c_int, [c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ovmr_f1_counts": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p]),
     "ovmr_fusion_weights": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),

@@ -505,6 +505,11 @@ int ovmr_head_fused(const void* feats_split, long long rows, const void* bank_cl
                           top_idx, top_val, S(stream));
 }
 
+int ovmr_head_fused_argmax(const void* feats_split, long long rows, const void* bank_class_major, int n_cls, int nseg,
+                           int operand_width, int* pred, void* stream) {
+  return ovmr::head_fused_argmax(feats_split, rows, bank_class_major, n_cls, nseg, operand_width, pred, S(stream));
+}
+
 int ovmr_argmax_segments(const float* logits, long long rows, long long ld, int seg_stride, int nseg, int n_cls, int* pred,
                          void* stream) {
   return ovmr::argmax_segments(logits, rows, ld, seg_stride, nseg, n_cls, pred, S(stream));

@@ -84,7 +84,11 @@ struct HeadArgs {
   float* top_val;
 };
 
-template <int NSEG, int KMAX>
+// ARGMAX: the exemplar self-classification of forward_prompt (trainers/mm_classifier_one_prompt.py:263-270) instead — ONE sweep,
+// each thread keeps (best logit, its first class) per segment and writes pred[q, s] = argmax_c logits_s[q, c] (ties -> lowest
+// index; a NaN row -> class 0): the [C S, 3 C] fp32 logits the reference materialises (22.9 GB at 21,841 classes x 4 shots)
+// never exist.
+template <int NSEG, int KMAX, bool ARGMAX>
 __global__ void __launch_bounds__(HF_THREADS, 1)
 head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HeadArgs ha) {
   extern __shared__ uint8_t smem_raw[];
@@ -104,6 +108,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int m_tiles = (ha.rows + HF_M - 1) / HF_M;
   const int n_tiles = (n_cols + HF_N - 1) / HF_N;
   const int k_blocks = ha.k_blocks;
+  const int sweeps = ARGMAX ? 1 : 2;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -134,7 +139,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== TMA producer: every (row tile, pass, class tile) in order =====================
     uint32_t stage = 0, phase = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
-      for (int pn = 0; pn < 2 * n_tiles; ++pn) {
+      for (int pn = 0; pn < sweeps * n_tiles; ++pn) {
         const int nt = pn < n_tiles ? pn : pn - n_tiles;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -154,7 +159,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t idesc = umma_idesc_16b_f32(HF_M, HF_N, 0);
     uint32_t stage = 0, phase = 0, iter = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
-      for (int pn = 0; pn < 2 * n_tiles; ++pn, ++iter) {
+      for (int pn = 0; pn < sweeps * n_tiles; ++pn, ++iter) {
         const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
@@ -190,7 +195,10 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float inv[NSEG];
       TopK<KMAX> top;
       top.init();
-      for (int pn = 0; pn < 2 * n_tiles; ++pn, ++iter) {
+      int best[NSEG];
+#pragma unroll
+      for (int s = 0; s < NSEG; ++s) best[s] = 0;
+      for (int pn = 0; pn < sweeps * n_tiles; ++pn, ++iter) {
         const bool emit = pn >= n_tiles;
         const int nt = emit ? pn - n_tiles : pn;
         const uint32_t as = iter & 1u, aphase = (iter >> 1) & 1u;
@@ -210,7 +218,19 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld32(taddr + HF_CHUNK * ch + 16, v + 16);
           tmem_ld_wait();
           const int n_valid = min(CPC, ha.n_cls - c0);         // classes of this chunk that exist
-          if (!emit) {
+          if (ARGMAX) {
+            // ---- single sweep: running (max, first index) per segment on the raw accumulators (scale > 0 keeps the order)
+#pragma unroll
+            for (int j = 0; j < CPC; ++j) {
+              if (j < n_valid) {
+#pragma unroll
+                for (int s = 0; s < NSEG; ++s) {
+                  const float x = __uint_as_float(v[j * NSEG + s]);
+                  if (x > mx[s]) { mx[s] = x; best[s] = c0 + j; }
+                }
+              }
+            }
+          } else if (!emit) {
             // ---- pass A: online (max, sum) per segment, log2 units
 #pragma unroll
             for (int s = 0; s < NSEG; ++s) {
@@ -252,7 +272,12 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
       }
-      if (q < ha.rows && ha.k > 0) {
+      if (ARGMAX) {
+        if (q < ha.rows) {
+#pragma unroll
+          for (int s = 0; s < NSEG; ++s) ha.top_idx[static_cast<long long>(q) * NSEG + s] = best[s];
+        }
+      } else if (q < ha.rows && ha.k > 0) {
 #pragma unroll
         for (int j = 0; j < KMAX; ++j) {
           if (j < ha.k) {
@@ -273,9 +298,9 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int NSEG, int KMAX>
+template <int NSEG, int KMAX, bool ARGMAX>
 int launch_head(const CUtensorMap& tmA, const CUtensorMap& tmB, const HeadArgs& ha, cudaStream_t stream) {
-  auto kern = head_fused_kernel<NSEG, KMAX>;
+  auto kern = head_fused_kernel<NSEG, KMAX, ARGMAX>;
   static PerDeviceOnce attr;
   if (attr.first()) OVMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HF_SMEM_BYTES));
   const int m_tiles = (ha.rows + HF_M - 1) / HF_M;
@@ -310,8 +335,28 @@ int head_fused(const void* feats_split, long long rows, const void* bank, int n_
   ha.top_val = top_val;
   // work = bytes the explicit form moved for the same rows (logits written and read back), for the head class's roofline line
   ProfScope prof(PROF_HEAD, static_cast<double>(rows) * (4.0 * nseg * n_cls + (probs ? 4.0 * n_cls : 0.0) + 8.0 * k), stream);
-  if (nseg == 3) return k <= 1 ? launch_head<3, 1>(tmA, tmB, ha, stream) : launch_head<3, 8>(tmA, tmB, ha, stream);
-  return k <= 1 ? launch_head<1, 1>(tmA, tmB, ha, stream) : launch_head<1, 8>(tmA, tmB, ha, stream);
+  if (nseg == 3) return k <= 1 ? launch_head<3, 1, false>(tmA, tmB, ha, stream) : launch_head<3, 8, false>(tmA, tmB, ha, stream);
+  return k <= 1 ? launch_head<1, 1, false>(tmA, tmB, ha, stream) : launch_head<1, 8, false>(tmA, tmB, ha, stream);
+}
+
+int head_fused_argmax(const void* feats_split, long long rows, const void* bank, int n_cls, int nseg, int k3e, int* pred,
+                      cudaStream_t stream) {
+  OVMR_REQUIRE(feats_split && bank && pred && rows > 0 && rows <= 0x7fffffffLL && n_cls > 0 && (nseg == 1 || nseg == 3),
+               "head_fused_argmax: rows=%lld n_cls=%d nseg=%d", rows, n_cls, nseg);
+  OVMR_REQUIRE(static_cast<long long>(n_cls) * nseg <= 0x7fffffffLL, "head_fused_argmax: too many classes");
+  OVMR_REQUIRE(k3e > 0 && k3e % 8 == 0, "head_fused_argmax: operand width %d must be a multiple of 8", k3e);
+  OVMR_REQUIRE((reinterpret_cast<uintptr_t>(feats_split) & 15) == 0 && (reinterpret_cast<uintptr_t>(bank) & 15) == 0,
+               "head_fused_argmax: operands must be 16-byte aligned");
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_16b(&tmA, feats_split, rows, k3e, k3e, HF_M);
+  if (rc) return rc;
+  rc = make_tmap_16b(&tmB, bank, static_cast<long long>(n_cls) * nseg, k3e, k3e, HF_N);
+  if (rc) return rc;
+  HeadArgs ha;
+  ha.rows = static_cast<int>(rows); ha.n_cls = n_cls; ha.nseg = nseg; ha.k_blocks = (k3e + HF_K - 1) / HF_K;
+  ha.scale_log2e = 1.f; ha.fusion_w = nullptr; ha.probs = nullptr; ha.ldp = 0; ha.k = 0; ha.top_idx = pred; ha.top_val = nullptr;
+  ProfScope prof(PROF_HEAD, static_cast<double>(rows) * 4.0 * nseg * n_cls, stream);
+  return nseg == 3 ? launch_head<3, 1, true>(tmA, tmB, ha, stream) : launch_head<1, 1, true>(tmA, tmB, ha, stream);
 }
 
 }  // namespace ovmr

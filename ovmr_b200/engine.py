@@ -373,6 +373,14 @@ def exemplar_counts(bank: ClassifierBank, feats: torch.Tensor, labels: torch.Ten
     counts = torch.zeros(2 * Cn * nseg + Cn, dtype=I32, device=dev)
     preds = torch.empty(R, nseg, dtype=I32, device=dev)
     labels = labels.to(device=dev, dtype=I32).contiguous()
+    if fused_head_enabled():
+        # one sweep on the tensor core: per-segment argmax kept in registers, no logits in HBM
+        a = bank.split_feats(feats)
+        L.check(lib.ovmr_head_fused_argmax(a.data_ptr(), R, bank.class_major().data_ptr(), Cn, nseg, 3 * bank.E, preds.data_ptr(),
+                                           L.stream()), "ovmr_head_fused_argmax")
+        L.check(lib.ovmr_f1_counts(preds.data_ptr(), labels.data_ptr(), R, nseg, Cn, counts.data_ptr(), L.stream()),
+                "ovmr_f1_counts")
+        return counts, preds
     # bound the logits chunk to ~1 GiB
     chunk = max(64, min(chunk, (1 << 28) // max(1, nseg * bank.Cpad)))
     for r0 in range(0, R, chunk):

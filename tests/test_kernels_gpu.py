@@ -469,6 +469,34 @@ def test_head_fused_kernel(R, Cn, E, k, nseg):
     assert torch.equal(idx[decided.squeeze(1)][:, 0], i3[decided.squeeze(1)][:, 0])
 
 
+@pytest.mark.parametrize("R,Cn,E", [(50, 37, 128), (600, 1000, 512), (333, 21841, 512)])
+@pytest.mark.parametrize("nseg", [3, 1])
+def test_head_fused_argmax_matches_explicit_head(R, Cn, E, nseg):
+    """Exemplar self-classification (trainers/mm_classifier_one_prompt.py:263-270) in one sweep: the per-segment argmax must
+    be the argmax of the logits the explicit path writes (same operands: bit-identical decisions, ties -> lowest index)."""
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(R + Cn + nseg)
+    nrm = torch.nn.functional.normalize
+    feats = nrm(torch.randn(R, E, generator=g), dim=-1)
+    cls = [nrm(torch.randn(Cn, E, generator=g), dim=-1) for _ in range(nseg)]
+    cls[0][5] = cls[0][2]                                  # an exact tie between classes 2 and 5 of segment 0
+    a, bank = _split_operands(feats, cls)
+    pred = torch.full((R, nseg), -7, dtype=torch.int32, device=DEV)
+    L.check(lib.ovmr_head_fused_argmax(a.data_ptr(), R, bank.data_ptr(), Cn, nseg, 3 * E, pred.data_ptr(), L.stream()))
+    Cpad = (Cn + 7) // 8 * 8
+    seg_bank = torch.zeros(nseg * Cpad, 3 * E, dtype=torch.bfloat16, device=DEV)
+    seg_bank.view(nseg, Cpad, 3 * E)[:, :Cn] = bank.view(Cn, nseg, 3 * E).permute(1, 0, 2)
+    lg = torch.empty(R, nseg * Cpad, device=DEV)
+    L.check(lib.ovmr_gemm_tn(a.data_ptr(), 3 * E, seg_bank.data_ptr(), 3 * E, R, nseg * Cpad, 3 * E, None, None, 0, lg.data_ptr(),
+                             nseg * Cpad, 0, 0, 1.0, 0, 0, 0, L.stream()))
+    ref = torch.empty(R, nseg, dtype=torch.int32, device=DEV)
+    L.check(lib.ovmr_argmax_segments(lg.data_ptr(), R, nseg * Cpad, Cpad, nseg, Cn, ref.data_ptr(), L.stream()))
+    torch.cuda.synchronize()
+    assert bool(((pred >= 0) & (pred < Cn)).all())
+    assert torch.equal(pred, ref), int((pred != ref).sum())
+    assert not bool((pred[:, 0] == 5).any())               # the tie always resolves to class 2
+
+
 def test_head_fused_ties_and_nan_rows():
     """Ties -> lowest class index; a NaN feature row gives NaN probabilities and in-range top-k indices."""
     L, lib = _lib()
