@@ -329,10 +329,20 @@ class ClassifierBank:
         return out
 
 
-def fused_head_enabled() -> bool:
-    """OVMR_FUSED_HEAD=0 selects the explicit head (logit GEMM -> fp32 logits in HBM -> fusion_softmax_topk kernel)."""
+FUSED_HEAD_MIN_ROWS = 12288
+
+
+def fused_head_enabled(rows: int) -> bool:
+    """Which head runs for `rows` feature rows.  The one-kernel head (ovmr_head_fused) parallelises over 128-row tiles only —
+    each CTA sweeps the whole class axis — so it needs >= ~96 tiles to fill the 148 SMs: measured 920 us against 1,547 us for
+    50,000 x 1,000 x 3, but 300 us against 16 us per 512-row call (profiles/r02_head.md).  Below FUSED_HEAD_MIN_ROWS the
+    explicit form runs (logit GEMM -> fp32 logits -> fusion_softmax_topk / argmax_segments; at that size the logits stay in L2).
+    OVMR_FUSED_HEAD=0 / 1 forces one form."""
     import os
-    return os.environ.get("OVMR_FUSED_HEAD", "1") != "0"
+    e = os.environ.get("OVMR_FUSED_HEAD")
+    if e in ("0", "1"):
+        return e == "1"
+    return rows >= FUSED_HEAD_MIN_ROWS
 
 
 def classify(bank: ClassifierBank, feats: torch.Tensor, scale: float, fusion_w: Optional[torch.Tensor], k: int = 1,
@@ -345,7 +355,7 @@ def classify(bank: ClassifierBank, feats: torch.Tensor, scale: float, fusion_w: 
     idx = torch.empty(R, max(k, 1), dtype=I32, device=dev)
     val = torch.empty(R, max(k, 1), dtype=F32, device=dev)
     fw = None if fusion_w is None else fusion_w.to(F32).contiguous()
-    if fused_head_enabled() and k <= 8 and scale > 0:
+    if fused_head_enabled(R) and k <= 8 and scale > 0:
         # one kernel: logit GEMM + softmaxes + fusion + top-k; the [R, nseg * C] logits are never written
         a = bank.split_feats(feats)
         L.check(lib.ovmr_head_fused(a.data_ptr(), R, bank.class_major().data_ptr(), bank.C, bank.nseg, 3 * bank.E, float(scale),
@@ -373,7 +383,7 @@ def exemplar_counts(bank: ClassifierBank, feats: torch.Tensor, labels: torch.Ten
     counts = torch.zeros(2 * Cn * nseg + Cn, dtype=I32, device=dev)
     preds = torch.empty(R, nseg, dtype=I32, device=dev)
     labels = labels.to(device=dev, dtype=I32).contiguous()
-    if fused_head_enabled():
+    if fused_head_enabled(R):
         # one sweep on the tensor core: per-segment argmax kept in registers, no logits in HBM
         a = bank.split_feats(feats)
         L.check(lib.ovmr_head_fused_argmax(a.data_ptr(), R, bank.class_major().data_ptr(), Cn, nseg, 3 * bank.E, preds.data_ptr(),

@@ -50,51 +50,41 @@ class PromptLearner(nn.Module):
 
     def __init__(self, cfg, classnames, clip_model):
         super().__init__()
-        n_cls = len(classnames)
-        n_ctx = cfg.TRAINER.COOP.N_CTX
-        ctx_init = cfg.TRAINER.COOP.CTX_INIT
-        dtype = torch.float32
-        ctx_dim = clip_model.ln_final.weight.shape[0]
-        clip_imsize = clip_model.visual.input_resolution
-        cfg_imsize = cfg.INPUT.SIZE[0]
-        assert cfg_imsize == clip_imsize, f"cfg_imsize ({cfg_imsize}) must equal to clip_imsize ({clip_imsize})"
+        coop = cfg.TRAINER.COOP
+        res_cfg, res_clip = cfg.INPUT.SIZE[0], clip_model.visual.input_resolution
+        assert res_cfg == res_clip, f"cfg_imsize ({res_cfg}) must equal to clip_imsize ({res_clip})"
         device = clip_model.visual.conv1.weight.device
         if device.type != "cuda":
             raise L.OvmrNativeError("PromptLearner: move the CLIP model to the CUDA device first (no CPU path)")
-        text = clip_model.text_engine(device)
+        embed = lambda text_or_tokens: clip_model.text_engine(device).embed(
+            clip.tokenize(text_or_tokens) if isinstance(text_or_tokens, str) else text_or_tokens).float()
 
-        if ctx_init:
-            ctx_init = ctx_init.replace("_", " ")
-            n_ctx = len(ctx_init.split(" "))
-            embedding = text.embed(clip.tokenize(ctx_init)).type(dtype)
-            ctx_vectors = embedding[0, 1:1 + n_ctx, :].clone()
-            prompt_prefix = ctx_init
+        # learned context: taken from a phrase (its token embeddings) or drawn N(0, 0.02), shared or per class (:96-117)
+        width = clip_model.ln_final.weight.shape[0]
+        phrase = (coop.CTX_INIT or "").replace("_", " ")
+        if phrase:
+            self.n_ctx = len(phrase.split(" "))
+            context = embed(phrase)[0, 1:1 + self.n_ctx].clone()
         else:
-            if cfg.TRAINER.COOP.CSC:
-                ctx_vectors = torch.empty(n_cls, n_ctx, ctx_dim, dtype=dtype)
-            else:
-                ctx_vectors = torch.empty(n_ctx, ctx_dim, dtype=dtype)
-            nn.init.normal_(ctx_vectors, std=0.02)
-            prompt_prefix = " ".join(["X"] * n_ctx)
-        self.ctx = nn.Parameter(ctx_vectors)
+            self.n_ctx = coop.N_CTX
+            phrase = " ".join("X" for _ in range(self.n_ctx))
+            context = torch.empty(*((len(classnames),) if coop.CSC else ()), self.n_ctx, width)
+            nn.init.normal_(context, std=0.02)
+        self.ctx = nn.Parameter(context)
 
-        classnames = [name.replace("_", " ") for name in classnames]
-        name_lens = [len(_tokenizer.encode(name)) for name in classnames]
-        prompts = [prompt_prefix + " " + name + "." for name in classnames]
-        tokenized_prompts = torch.cat([clip.tokenize(p) for p in prompts])
-        embedding = text.embed(tokenized_prompts).type(dtype)
-        visual_template = text.embed(clip.tokenize(prompt_prefix + ".")).type(dtype)
-        self.register_buffer("visual_template", visual_template)
-        visual_tokens = torch.load(cfg.TRAINER.COOP.VISUAL_TOKEN_PATH, map_location="cpu")["visual_tokens"]
-        self.visual_tokens_len = visual_tokens.shape[1]
-        self.register_buffer("token_visual", visual_tokens.to(dtype))
-        self.register_buffer("token_prefix", embedding[:, :1, :])           # SOS
-        self.register_buffer("token_suffix", embedding[:, 1 + n_ctx:, :])   # CLS, EOS
-        self.n_cls = n_cls
-        self.n_ctx = n_ctx
-        self.tokenized_prompts = tokenized_prompts
-        self.name_lens = name_lens
-        self.class_token_position = cfg.TRAINER.COOP.CLASS_TOKEN_POSITION
+        # frozen pieces of every prompt: SOS | <context> | [visual tokens] | class name, ".", EOS, padding (:123-150)
+        names = [n.replace("_", " ") for n in classnames]
+        self.n_cls = len(names)
+        self.name_lens = [len(_tokenizer.encode(n)) for n in names]
+        self.tokenized_prompts = torch.cat([clip.tokenize(f"{phrase} {n}.") for n in names])
+        rows = embed(self.tokenized_prompts)
+        self.register_buffer("visual_template", embed(phrase + "."))
+        vtok = torch.load(coop.VISUAL_TOKEN_PATH, map_location="cpu")["visual_tokens"].float()
+        self.visual_tokens_len = vtok.shape[1]
+        self.register_buffer("token_visual", vtok)
+        self.register_buffer("token_prefix", rows[:, :1])                  # SOS
+        self.register_buffer("token_suffix", rows[:, 1 + self.n_ctx:])     # class tokens, EOS, padding
+        self.class_token_position = coop.CLASS_TOKEN_POSITION
         self.to(device)
 
     def forward(self):

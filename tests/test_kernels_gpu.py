@@ -497,6 +497,33 @@ def test_head_fused_argmax_matches_explicit_head(R, Cn, E, nseg):
     assert not bool((pred[:, 0] == 5).any())               # the tie always resolves to class 2
 
 
+def test_engine_head_forms_agree(monkeypatch):
+    """ovmr_b200.engine routes the head by row count (one kernel from FUSED_HEAD_MIN_ROWS rows on, explicit below): both forms,
+    forced through the same engine calls, must give the same exemplar predictions / F1 counts and the same fused top-k."""
+    from ovmr_b200 import engine as Eng
+    g = torch.Generator().manual_seed(21)
+    nrm = torch.nn.functional.normalize
+    Cn, S, E = 300, 4, 512
+    cls = [nrm(torch.randn(Cn, E, generator=g), dim=-1).to(DEV) for _ in range(3)]
+    labels = torch.arange(Cn).repeat_interleave(S)
+    feats = nrm(cls[0].cpu()[labels] + 0.8 * torch.randn(Cn * S, E, generator=g), dim=-1).to(DEV)
+    bank = Eng.ClassifierBank(cls)
+    out = {}
+    for form in ("0", "1"):
+        monkeypatch.setenv("OVMR_FUSED_HEAD", form)
+        counts, preds = Eng.exemplar_counts(bank, feats, labels, 100.0)
+        w, f1 = Eng.fusion_weights_from_counts(counts, 3, Cn, 10.0)
+        probs, idx, val = Eng.classify(bank, feats, 100.0, w, k=5, want_probs=True)
+        torch.cuda.synchronize()
+        out[form] = (counts.cpu(), preds.cpu(), w.cpu(), probs.cpu(), idx.cpu(), val.cpu())
+    monkeypatch.delenv("OVMR_FUSED_HEAD")
+    assert not Eng.fused_head_enabled(512) and Eng.fused_head_enabled(50000)
+    a, b = out["0"], out["1"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert (a[3] - b[3]).abs().max() < 2e-6 + 1e-4 * float(a[3].max())
+    assert torch.equal(a[4][:, 0], b[4][:, 0])
+
+
 def test_head_fused_ties_and_nan_rows():
     """Ties -> lowest class index; a NaN feature row gives NaN probabilities and in-range top-k indices."""
     L, lib = _lib()
