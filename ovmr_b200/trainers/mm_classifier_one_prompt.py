@@ -150,7 +150,7 @@ class PromptLearner(nn.Module):
 class CustomCLIP(nn.Module):
     """trainers/...:179-364."""
 
-    GEN_GROUP = 128   # classes per aggregator / text-tower pass in forward_prompt
+    GEN_GROUP = int(os.environ.get("OVMR_GEN_GROUP", "128"))   # classes per aggregator / text-tower pass in forward_prompt
 
     def __init__(self, cfg, classnames, clip_model, shard=None):
         super().__init__()
