@@ -150,7 +150,9 @@ class PromptLearner(nn.Module):
 class CustomCLIP(nn.Module):
     """trainers/...:179-364."""
 
-    GEN_GROUP = int(os.environ.get("OVMR_GEN_GROUP", "128"))   # classes per aggregator / text-tower pass in forward_prompt
+    # classes per aggregator / text-tower pass in forward_prompt (config 3, N = 1: 128 -> 512 classes per pass = 48k -> 20k launches
+    # per step, 23.6k -> 23.9k img/s; the result does not depend on the grouping)
+    GEN_GROUP = int(os.environ.get("OVMR_GEN_GROUP", "512"))
 
     def __init__(self, cfg, classnames, clip_model, shard=None):
         super().__init__()
