@@ -178,6 +178,12 @@ int ovmr_attention_impl(const void* qkv, void* out, int n_seq, int seq_len, int 
  * positional_embedding[1 + t] and writes patch t of image b to row b * (G*G + 1) + 1 + t of x fp32 [batch * (G*G + 1), width]
  * (CLS rows untouched).  conv_w: conv1.weight.reshape(D, -1), 16-bit [width, k_pad], zero padded.  This is what the vision
  * tower runs; ovmr_patchify(_u8) + ovmr_gemm_tn remain as the explicit form (OVMR_IMPLICIT_PATCH=0). */
+/* Host-only check behind the uint8 entry points: 1 when the division-free form of ToTensor + Normalize the kernels use
+ * (q = a * r; q += fma(-b, q, a) * r with r = RN(1 / b), for /255 and /std) returns the very bits of the two IEEE divisions for
+ * all 768 (channel, byte) pairs of this mean / std (HOST pointer to 6 floats), else 0 — the kernels then keep the divisions
+ * (ovmr_patchify_u8) or refuse (ovmr_patch_embed).  No GPU needed. */
+int ovmr_u8_normalization_is_exact(const float* mean_std);
+
 int ovmr_patch_embed(const void* images, int is_u8, const float* mean_std, int batch, int resolution, int patch,
                      const void* conv_w, int k_pad, const float* positional_embedding, float* x, int width, int fp16,
                      void* stream);

@@ -66,6 +66,7 @@ SIGNATURES = {
                                c_void_p, c_ll, c_void_p, c_void_p, c_int, c_void_p]),
     "ovmr_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ovmr_attention_impl": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ovmr_u8_normalization_is_exact": (c_int, [C.POINTER(c_float)]),
     "ovmr_patch_embed": (c_int, [c_void_p, c_int, C.POINTER(c_float), c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                  c_int, c_int, c_void_p]),
     "ovmr_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -449,6 +449,8 @@ int ovmr_attention_impl(const void* qkv, void* out, int n_seq, int seq_len, int 
   return ovmr::attention(qkv, out, n_seq, seq_len, width, heads, causal, fp16 != 0, S(stream), 0, impl);
 }
 
+int ovmr_u8_normalization_is_exact(const float* mean_std) { return ovmr::patch_embed_u8_exact(mean_std) ? 1 : 0; }
+
 int ovmr_patch_embed(const void* images, int is_u8, const float* mean_std, int batch, int resolution, int patch,
                      const void* conv_w, int k_pad, const float* positional_embedding, float* x, int width, int fp16, void* stream) {
   OVMR_REQUIRE(!is_u8 || mean_std != nullptr, "patch_embed: uint8 input needs mean / std");

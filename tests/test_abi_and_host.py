@@ -156,3 +156,62 @@ def test_bench_reference_arm_prints_the_contract_line():
     # --shots 2 is not a BASELINE shape: metric and workload strings must say so instead of claiming config 2
     assert "x 2 shot" in line["metric"] and line["config"]["workload"].startswith("CUSTOM shape")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+
+def test_u8_normalization_exactness_check_matches_exact_rational_arithmetic():
+    """The host check that licenses the division-free ToTensor + Normalize in the uint8 kernels (q = a r; q += fma(-b, q, a) r):
+    its verdict for CLIP's mean / std (clip/clip.py:79) and for a spread of other constants must equal an independent
+    evaluation of the same formula in exact rational arithmetic with correct rounding to fp32 (no GPU involved)."""
+    import ctypes as C
+    from fractions import Fraction as F
+
+    import numpy as np
+    from ovmr_b200 import _lib as L
+    lib = L.load()
+
+    def rn(x):      # round a Fraction to the nearest float32 (ties to even via numpy on the two neighbours)
+        y = np.float32(float(x))
+        cands = [y, np.nextafter(y, np.float32(np.inf)), np.nextafter(y, np.float32(-np.inf))]
+        return min(cands, key=lambda c: (abs(F(float(c)) - x), int(np.float32(c).view(np.uint32)) & 1))
+
+    def fma(a, b, c):
+        return rn(F(float(a)) * F(float(b)) + F(float(c)))
+
+    def exact(mean_std):
+        f32 = np.float32
+        for c in range(3):
+            m, sd = f32(mean_std[c]), f32(mean_std[3 + c])
+            rsd, r255 = f32(1.0) / sd, f32(1.0) / f32(255.0)
+            for v in range(256):
+                f = f32(v)
+                ref = ((f / f32(255.0)) - m) / sd
+                t = f * r255
+                t = fma(fma(f32(-255.0), t, f), r255, t)
+                u = t - m
+                y = u * rsd
+                y = fma(fma(-sd, y, u), rsd, y)
+                if y != ref:
+                    return 0
+        return 1
+
+    clip_ms = [0.48145466, 0.4578275, 0.40821073, 0.26862954, 0.26130258, 0.27577711]
+    assert lib.ovmr_u8_normalization_is_exact((C.c_float * 6)(*clip_ms)) == 1 == exact(clip_ms)
+    rng = np.random.default_rng(0)
+    for _ in range(6):
+        ms = list(rng.uniform(0.2, 0.6, 3)) + list(rng.uniform(0.05, 0.6, 3))
+        assert lib.ovmr_u8_normalization_is_exact((C.c_float * 6)(*ms)) == exact(ms), ms
+    assert lib.ovmr_u8_normalization_is_exact((C.c_float * 6)(0.5, 0.5, 0.5, 0.0, 0.2, 0.2)) == 0     # std must be positive
+
+
+def test_head_routing_by_row_count(monkeypatch):
+    """ovmr_b200.engine picks the one-kernel head from FUSED_HEAD_MIN_ROWS feature rows on, the explicit head below;
+    OVMR_FUSED_HEAD forces one form."""
+    from ovmr_b200 import engine as Eng
+    monkeypatch.delenv("OVMR_FUSED_HEAD", raising=False)
+    assert not Eng.fused_head_enabled(512) and not Eng.fused_head_enabled(Eng.FUSED_HEAD_MIN_ROWS - 1)
+    assert Eng.fused_head_enabled(Eng.FUSED_HEAD_MIN_ROWS) and Eng.fused_head_enabled(87364)
+    monkeypatch.setenv("OVMR_FUSED_HEAD", "1")
+    assert Eng.fused_head_enabled(1)
+    monkeypatch.setenv("OVMR_FUSED_HEAD", "0")
+    assert not Eng.fused_head_enabled(10 ** 6)
