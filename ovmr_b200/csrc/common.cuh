@@ -304,6 +304,17 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtens
       : "memory");
 }
 
+// The same, MULTICAST to every CTA of `cta_mask`: the box lands at this smem offset in each of them and the bytes are signalled
+// on the mbarrier of each destination's pair leader.
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int32_t c0, int32_t c1,
+                                                    uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------

@@ -864,7 +864,9 @@ __device__ long long g_rowln_trace[3][RT_TILES][RT_EVENTS];   // [epilogue warp 
 //             persistent grid whose CTAs are all co-resident, and the partials travel through a global (L2) scratch with
 //             release / acquire counters.  A cluster of 6 (8) CTAs must sit inside one GPC, so only 22 (16) of them fit a
 //             B200 (132 / 128 of 148 SMs); pairs fit everywhere: 24 (18) groups, 144 SMs.
-template <int NT, bool GX, int SB>
+// MC (cluster form only): the NT pairs of a row block read the SAME A rows, so each A box is fetched once and multicast to
+// the NT CTAs of the same M half (the pairs take turns by K block); a stage is then free only when all NT pairs have consumed it.
+template <int NT, bool GX, int SB, bool MC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -900,6 +902,11 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int row_blocks = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   const uint16_t pair_mask = static_cast<uint16_t>(3u << (2u * (rank >> 1)));
+  constexpr bool MCAST = MC && !GX;
+  const uint16_t all_mask = static_cast<uint16_t>((1u << (2 * NT)) - 1u);
+  uint16_t half_mask = 0;    // the CTAs that hold the same 128 A rows as this one
+#pragma unroll
+  for (int p = 0; p < NT; ++p) half_mask |= static_cast<uint16_t>(1u << (2 * p + static_cast<int>(half)));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -911,7 +918,7 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 2);    // leader: arrive.expect_tx (own) + remote arrive (peer producer)
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), MCAST ? NT : 1);   // multicast: one commit per pair of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -946,7 +953,11 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
-          tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
+          if (MCAST) {
+            if (kb % NT == static_cast<int>(pair)) tma_load_2d_pair_mc(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0, half_mask);
+          } else {
+            tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
+          }
           tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * BLOCK_K, n0);
           if (!leader) mbar_arrive_remote(full_bar(stage), leader_rank);
           // (the NT pairs of a row block read the same A rows: only the first pair prefetches them)
@@ -978,7 +989,8 @@ gemm_tn_rowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
               umma_16b_ss_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit_pair_mc(empty_bar(stage), pair_mask);          // frees this stage in both CTAs of the pair
+            // frees this stage in both CTAs of the pair — or, under A multicast, counts towards freeing it everywhere
+            umma_commit_pair_mc(empty_bar(stage), MCAST ? all_mask : pair_mask);
             if (kb == k_blocks - 1) umma_commit_pair_mc(tfull_bar(as), pair_mask);
           }
           __syncwarp();
@@ -1564,7 +1576,7 @@ int launch_pair(const void* A, long long lda, const void* B, long long ldb, int 
   return 0;
 }
 
-template <int NT, bool GX, int SB>
+template <int NT, bool GX, int SB, bool MC>
 int launch_rowln(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                  const GemmEpilogue& ep, cudaStream_t stream) {
   using Cfg = RowLnCfg<NT, SB>;
@@ -1574,7 +1586,7 @@ int launch_rowln(const void* A, long long lda, const void* B, long long ldb, int
   if (rc) return rc;
   rc = make_tmap_2d(&mp.c16, ep.ln_out, 2, M, N, ep.ld_ln, 32, 64);
   if (rc) return rc;
-  auto kern = gemm_tn_rowln_kernel<NT, GX, SB>;
+  auto kern = gemm_tn_rowln_kernel<NT, GX, SB, MC>;
   static PerDeviceOnce attr;
   static PerDeviceSize max_groups;   // co-resident row-block groups of 2 NT CTAs (one CTA per SM) on this device
   if (attr.first()) {
@@ -1785,13 +1797,20 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, int M, i
     if (ep.ln_scratch != nullptr) {
       OVMR_REQUIRE((reinterpret_cast<uintptr_t>(ep.ln_scratch) & 15) == 0 && ep.ln_gen > 0 && ep.ln_gen < (1u << 24),
                    "gemm: the global LayerNorm exchange needs an aligned scratch and a generation in [1, 2^24)");
-      if (N == 512) return launch_rowln<2, true, 2>(A, lda, B, ldb, M, N, K, ep, stream);
-      if (N == 768) return launch_rowln<3, true, 2>(A, lda, B, ldb, M, N, K, ep, stream);
-      return launch_rowln<4, true, 2>(A, lda, B, ldb, M, N, K, ep, stream);
+      if (N == 512) return launch_rowln<2, true, 2, false>(A, lda, B, ldb, M, N, K, ep, stream);
+      if (N == 768) return launch_rowln<3, true, 2, false>(A, lda, B, ldb, M, N, K, ep, stream);
+      return launch_rowln<4, true, 2, false>(A, lda, B, ldb, M, N, K, ep, stream);
     }
-    if (N == 512) return launch_rowln<2, false, 2>(A, lda, B, ldb, M, N, K, ep, stream);
-    if (N == 768) return launch_rowln<3, false, 2>(A, lda, B, ldb, M, N, K, ep, stream);
-    return launch_rowln<4, false, 2>(A, lda, B, ldb, M, N, K, ep, stream);
+    // OVMR_ROWLN_MCAST=1: A boxes multicast across the pairs of the cluster (A/B measurements)
+    static const bool mcast = [] { const char* e = getenv("OVMR_ROWLN_MCAST"); return e != nullptr && e[0] == '1'; }();
+    if (mcast) {
+      if (N == 512) return launch_rowln<2, false, 2, true>(A, lda, B, ldb, M, N, K, ep, stream);
+      if (N == 768) return launch_rowln<3, false, 2, true>(A, lda, B, ldb, M, N, K, ep, stream);
+      return launch_rowln<4, false, 2, true>(A, lda, B, ldb, M, N, K, ep, stream);
+    }
+    if (N == 512) return launch_rowln<2, false, 2, false>(A, lda, B, ldb, M, N, K, ep, stream);
+    if (N == 768) return launch_rowln<3, false, 2, false>(A, lda, B, ldb, M, N, K, ep, stream);
+    return launch_rowln<4, false, 2, false>(A, lda, B, ldb, M, N, K, ep, stream);
   }
   if (tma_resid) return dispatch_tile<EPI_F32_RESID>(bn, A, lda, B, ldb, M, N, K, ep, stream);
   static const bool tma_scatter = [] { const char* e = getenv("OVMR_TMA_SCATTER"); return e == nullptr || e[0] != '0'; }();
