@@ -774,12 +774,11 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //   pass 2  once the 2 NT partials of its rows are in, a warp combines them (Chan), reads x' back from TMEM, applies
 //           (x' - mean) * rstd * gamma + beta, packs to 16 bits and TMA-stores the LayerNorm rows.
 // The LayerNorm kernel and its 4D-byte read of x' disappear; the 2D-byte write is the one the LayerNorm kernel made.
-// SB staging boxes per epilogue warp (2 or 3) and the smem ring that goes with them.  A warp's pass 1 is a chain of residual
-// boxes (TMA load -> add in place -> TMA store): with two boxes the load of chunk c + 1 can only be issued once the store of
-// chunk c - 1 has been read out, and its ~2000 cycles of latency are exposed on every chunk (profiles/r02_rowln_trace.md:
-// ~2000 cycles per chunk against ~500 of instructions).  With three boxes the first three chunks of a tile are requested
-// before the accumulator is even ready.  The third box costs one main-loop stage: used for K <= 1024 (out-proj: 12-16
-// K blocks per tile, epilogue-bound), not for c_proj (K = 4 D, main-loop-bound).
+// SB staging boxes per epilogue warp and the smem ring that goes with them.  A warp's pass 1 is a chain of residual boxes
+// (TMA load -> add in place -> TMA store): the first SB chunks of a tile are requested before its accumulator is ready, chunk
+// c + SB - 1 once the store of chunk c - 1 has been read out.  SB = 2 (4 ring stages) is what runs; SB = 3 (third box paid for
+// with a ring stage) compiles but was measured no faster at K = 768 and slower at K = 3072 (profiles/r02_rowln_trace.md: chunks
+// whose residual is already resident still take 1,500-1,800 cycles) and is not instantiated.
 template <int NT, int SB>
 struct RowLnCfg {
   static constexpr int STAGES = SB == 3 ? 3 : 4;
