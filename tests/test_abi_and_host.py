@@ -136,6 +136,33 @@ def test_plan_batches_partitions_exactly_and_respects_cap():
             off += z
 
 
+def test_plan_batches_wave_model_choices():
+    """The planner compares 'full batches + ragged tail' with 'even split' under a wave model of the persistent GEMMs: it must
+    never pick the costlier candidate, must keep a 512-image ViT-B/16 batch whole (394 row blocks = 47.9 / 63.9 / 17.9 waves:
+    already within 0.5 % of whole waves), and must behave for the ViT-L geometry (577 tokens, width 1024: residual GEMMs on the
+    CTA pairs, not on row-block clusters)."""
+    from ovmr_b200.data import plan_batches
+
+    def waves(z, tokens, width):
+        mp = -(-z * tokens // 256)
+        nt = width // 256
+        c = -(-mp * 3 * nt // 74) + -(-mp * 4 * nt // 74)
+        c += (-(-mp // 22) if width <= 768 else -(-mp * nt // 74)) * 5
+        return c
+
+    for n, cap, tokens, width in ((8250, 512, 197, 768), (2000, 512, 197, 768), (6250, 256, 577, 1024), (16000, 512, 197, 768),
+                                  (87364, 512, 197, 768), (777, 256, 577, 1024)):
+        plan = plan_batches(n, cap, tokens_per_image=tokens, width=width)
+        sizes = [z for _, z in plan]
+        k = -(-n // cap)
+        even = [n // k + (1 if i < n % k else 0) for i in range(k)]
+        ragged = [cap] * (n // cap) + ([n % cap] if n % cap else [])
+        cost = lambda zs: sum(waves(z, tokens, width) for z in zs)
+        assert sizes in (even, ragged)
+        assert cost(sizes) == min(cost(even), cost(ragged))
+    assert [z for _, z in plan_batches(1024, 512)] == [512, 512]
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """bench.py --impl reference (the reference's own CPU implementation on the host cores — its unmodified code when
     /root/reference or oracle/_ref is present, else the oracle port): one JSON line with the contract keys, labelled
